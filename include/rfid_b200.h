@@ -1,0 +1,201 @@
+/* rfid_b200.h -- C-ABI of the B200-native Gen2 receive/decode chain.
+ *
+ * This is the drop-in boundary: a plain-C shared library (librfid_b200.so) whose
+ * entry points are what the reference's three GNU Radio blocks would bind if
+ * their work() loops were replaced by GPU calls.  Nothing like it exists in the
+ * reference (it has no FFI); each entry point cites the reference interface it
+ * replaces (paths relative to /root/reference/gr-rfid).
+ *
+ *   reference                                   | replaced by
+ *   --------------------------------------------+--------------------------------------
+ *   filter.fir_filter_ccc(5,[1]*25)             | rfid_b200_mf_work      (block mode)
+ *     apps/reader.py:65,75 (GNU Radio, external)|   + fused into rfid_b200_decode_capture
+ *   gate_impl::general_work  lib/gate_impl.cc:85| rfid_b200_gate_work    (block mode)
+ *   tag_decoder_impl::general_work              | rfid_b200_decoder_work (block mode)
+ *     lib/tag_decoder_impl.cc:196               |
+ *   whole RX chain on a recorded capture        | rfid_b200_decode_capture (capture mode)
+ *   READER_STATS bookkeeping                    | rfid_b200_reduce_stats
+ *     lib/tag_decoder_impl.cc:269-288,329-387   |
+ *
+ * Conventions: every function returns 0 on success or a negative RFID_B200_E*
+ * code (rfid_b200_strerror() names it); no exception crosses the boundary; no
+ * torch/C++ types appear in a signature.  Complex samples are interleaved
+ * float32 I,Q (GNU Radio gr_complex / the on-disk format of
+ * misc/data/file_source_test, apps/reader.py:102).  There is NO CPU fallback:
+ * rfid_b200_create() fails with RFID_B200_ENODEV when no sm_100 device is
+ * usable.
+ */
+#ifndef RFID_B200_H
+#define RFID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFID_B200_API __attribute__((visibility("default")))
+
+#define RFID_B200_ABI_VERSION 1
+
+/* error codes */
+enum {
+  RFID_B200_OK = 0,
+  RFID_B200_EINVAL = -1,   /* bad argument */
+  RFID_B200_ENODEV = -2,   /* no usable sm_100 CUDA device */
+  RFID_B200_ENOMEM = -3,   /* host or device allocation failed */
+  RFID_B200_ECUDA = -4,    /* CUDA runtime error (see rfid_b200_last_cuda_error) */
+  RFID_B200_ECAPACITY = -5 /* caller-provided output buffer too small */
+};
+
+/* window kinds (reference: DECODER_DECODE_RN16 / DECODER_DECODE_EPC, include/rfid/global_vars.h:34) */
+enum { RFID_B200_RN16 = 0, RFID_B200_EPC = 1 };
+
+/* Configuration.  Defaults reproduce apps/reader.py:52-65 + include/rfid/global_vars.h:72-143. */
+typedef struct rfid_b200_params {
+  int32_t adc_rate;    /* raw complex sample rate, Hz            (reader.py:53  -> 2000000) */
+  int32_t decim;       /* matched-filter decimation              (reader.py:54  -> 5)       */
+  int32_t ntaps;       /* boxcar length = half an FM0 symbol     (reader.py:65  -> 25)      */
+  int32_t fixed_q;     /* slots per round = 2^fixed_q            (global_vars.h:72 -> 0)    */
+  int32_t max_queries; /* stop after this many Query/QueryRep    (global_vars.h:76 -> 1000) */
+  int32_t max_tags;    /* stop after more than this many unique tags (global_vars.h:100 -> 100) */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t reserved;
+} rfid_b200_params;
+
+/* One capture segment: a contiguous range of RAW samples that is decoded as an
+ * independent stream with freshly constructed gate state. */
+typedef struct rfid_b200_segment {
+  uint64_t offset; /* first raw complex sample */
+  uint32_t length; /* number of raw complex samples */
+  uint32_t reserved;
+} rfid_b200_segment;
+
+/* One decoded window (64 bytes).  Everything the reference's tag_decoder
+ * derives from one ungated window, including the quantities it keeps private
+ * (score = local `max` in tag_sync, tag_decoder_impl.cc:81,94-98). */
+typedef struct rfid_b200_window_result {
+  int32_t segment;    /* index into the segment table */
+  int32_t window;     /* ordinal inside the segment: even = RN16, odd = EPC */
+  int32_t open_index; /* decimated index (segment relative) of the first ungated sample, gate_impl.cc:164-175 */
+  int32_t length;     /* n_samples_to_ungate, gate_impl.cc:115,121 */
+  int32_t kind;       /* RFID_B200_RN16 / RFID_B200_EPC */
+  int32_t sync_index; /* argmax offset of the preamble correlation, tag_decoder_impl.cc:85-100 */
+  float score;        /* |c(sync_index)|^2, tag_decoder_impl.cc:94 */
+  float h_re, h_im;   /* channel estimate h_est, tag_decoder_impl.cc:103 */
+  float T;            /* EPC half-symbol period T_global, tag_decoder_impl.cc:166-169; 0 for RN16 */
+  int32_t crc_ok;     /* EPC: 1 pass / 0 fail (check_crc, tag_decoder_impl.cc:401-445); RN16: -1 */
+  int32_t tag_id;     /* EPC: bits[104..111] as an integer, tag_decoder_impl.cc:348-352; RN16: the 16-bit RN16 */
+  uint8_t bits[16];   /* decoded bits, MSB first; RN16 uses bits[0..1], EPC all 16 bytes */
+} rfid_b200_window_result;
+
+/* READER_STATS as a plain struct (include/rfid/global_vars.h:36-53). */
+#define RFID_B200_MAX_TAGS 256
+typedef struct rfid_b200_stats {
+  int32_t n_queries_sent;
+  int32_t cur_inventory_round;
+  int32_t cur_slot_number;
+  int32_t max_slot_number;
+  int32_t n_epc_correct;
+  int32_t n_windows;      /* windows that entered the statistics */
+  int32_t terminated;     /* 1 once the reference's stop rule fired, gate_impl.cc:101-109 */
+  int32_t n_unique_tags;
+  int32_t tag_id[RFID_B200_MAX_TAGS];    /* ascending (std::map order) */
+  int32_t tag_reads[RFID_B200_MAX_TAGS];
+} rfid_b200_stats;
+
+typedef struct rfid_b200_ctx rfid_b200_ctx;
+
+RFID_B200_API int rfid_b200_abi_version(void);
+RFID_B200_API const char* rfid_b200_strerror(int code);
+RFID_B200_API const char* rfid_b200_last_cuda_error(const rfid_b200_ctx* ctx);
+RFID_B200_API void rfid_b200_default_params(rfid_b200_params* p);
+
+/* Context: one per block instance (block mode) or per decode stream (capture mode).
+ * Replaces the constructors gate_impl.cc:41-70 / tag_decoder_impl.cc:50-62 and the
+ * process-global reader_state (global_vars.cc:34-54). */
+RFID_B200_API int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out);
+RFID_B200_API void rfid_b200_destroy(rfid_b200_ctx* ctx);
+
+/* Derived sample counts (gate_impl.cc:48-53,115,121; tag_decoder_impl.cc:60). */
+RFID_B200_API int rfid_b200_window_length(const rfid_b200_ctx* ctx, int kind);
+RFID_B200_API int rfid_b200_fs_dec(const rfid_b200_ctx* ctx);
+
+/* ---------------- capture mode (throughput path) ----------------
+ * Decode nseg independent segments of a raw capture that is ALREADY RESIDENT in
+ * device memory: matched filter + decimation, gate, tag_decoder, all on the GPU,
+ * asynchronously on `stream` (a cudaStream_t passed as void*; NULL = default).
+ * d_iq: device pointer, interleaved float32 I,Q.  d_segs: device pointer to nseg
+ * segment descriptors.  d_results: device buffer of nseg*max_windows_per_segment
+ * records; record k of segment s lands at d_results[s*max_windows_per_segment+k].
+ * d_counts: device int32[nseg], number of windows found per segment.
+ * Windows beyond max_windows_per_segment are counted but not stored. */
+RFID_B200_API int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw,
+                                           const rfid_b200_segment* d_segs, int nseg,
+                                           int max_windows_per_segment,
+                                           rfid_b200_window_result* d_results, int32_t* d_counts,
+                                           void* stream);
+
+/* Same, but every pointer is a HOST pointer: copies in, decodes, copies the
+ * records out, synchronises.  This is the end-to-end call a reference user makes
+ * on a recorded file (apps/reader.py:102-112 in DEBUG mode). */
+RFID_B200_API int rfid_b200_decode_capture_host(rfid_b200_ctx* ctx, const float* h_iq, size_t n_raw,
+                                                const rfid_b200_segment* h_segs, int nseg,
+                                                int max_windows_per_segment,
+                                                rfid_b200_window_result* h_results, int32_t* h_counts);
+
+/* Kernel launches issued by the last decode_capture call on this context. */
+RFID_B200_API int rfid_b200_last_launch_count(const rfid_b200_ctx* ctx);
+/* Device time (ms, CUDA events on the launch stream) of the dominant kernel
+ * (fused matched-filter+gate) accumulated since the last reset; and its launches. */
+RFID_B200_API int rfid_b200_kernel_time(rfid_b200_ctx* ctx, int reset, float* ms_total, int* launches);
+RFID_B200_API int rfid_b200_enable_kernel_timing(rfid_b200_ctx* ctx, int on);
+
+/* Optional debug taps for capture mode (device pointers, may be NULL):
+ * d_windows receives the ungated, DC-removed samples of every stored window
+ * (gate output, gate_impl.cc:173,187) at a stride of rfid_b200_window_length(EPC)
+ * complex samples per record slot. */
+RFID_B200_API int rfid_b200_set_window_tap(rfid_b200_ctx* ctx, float* d_windows);
+
+/* Host-side reduction of window records into READER_STATS, replaying the
+ * bookkeeping of tag_decoder_impl.cc:269-288,295,329-387 and the stop rule of
+ * gate_impl.cc:101-109 in stream order.  `continuous` != 0: all records belong to
+ * one continuous reader session (counters carry across segments);
+ * 0: every segment is its own session and the per-session stats are summed. */
+RFID_B200_API int rfid_b200_reduce_stats(const rfid_b200_ctx* ctx, const rfid_b200_window_result* h_results,
+                                         const int32_t* h_counts, int nseg, int max_windows_per_segment,
+                                         int continuous, rfid_b200_stats* out);
+
+/* ---------------- block mode (GNU Radio drop-in) ----------------
+ * Called from the thin host blocks' general_work(); HOST pointers, owned by the
+ * scheduler, touched only during the call.  State lives in the context (device
+ * memory) between calls. */
+
+/* gate_impl::general_work (gate_impl.cc:85-200).  seek: 0 = none, 1 = the Gen2
+ * logic asked for an RN16 window, 2 = for an EPC window since the previous call
+ * (reader_state->gate_status SEEK flags, gate_impl.cc:112-123).  Returns through
+ * *consumed / *written the values the reference passes to consume_each() and
+ * returns; *closed = 1 when a window completed inside this call.  magn2_out
+ * (may be NULL) receives |out|^2 per written sample (reader_state->magn_squared_samples). */
+RFID_B200_API int rfid_b200_gate_work(rfid_b200_ctx* ctx, int seek, const float* in, int n_in, float* out,
+                                      int out_capacity, int* consumed, int* written, int* closed,
+                                      float* magn2_out);
+
+/* tag_decoder_impl::general_work on one complete window (tag_decoder_impl.cc:223-393):
+ * win = n complex samples (n >= window length of `kind`), result in *res.
+ * bits_out (may be NULL): 16 (RN16) or 128 (EPC) floats in {0.,1.} exactly as the
+ * reference writes them to stream port 0 (tag_decoder_impl.cc:261-266). */
+RFID_B200_API int rfid_b200_decoder_work(rfid_b200_ctx* ctx, int kind, const float* win, int n,
+                                         rfid_b200_window_result* res, float* bits_out);
+
+/* fir_filter_ccc(decim,[1]*ntaps) replacement (apps/reader.py:75): canonical
+ * boxcar + decimation with ntaps-1 samples of history kept in the context.
+ * Writes floor((n_in + carry)/decim) outputs. */
+RFID_B200_API int rfid_b200_mf_work(rfid_b200_ctx* ctx, const float* in, int n_in, float* out, int out_capacity,
+                                    int* written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFID_B200_H */
