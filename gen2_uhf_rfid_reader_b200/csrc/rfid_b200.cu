@@ -1,0 +1,505 @@
+// rfid_b200.cu -- C-ABI of the B200-native Gen2 receive chain (see include/rfid_b200.h).
+// Host side: context, configuration derivation, launches, host<->device marshalling,
+// READER_STATS reduction.  There is no CPU implementation of the signal path in this
+// library: every entry point that produces samples or decisions launches a kernel.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rx_block.cuh"
+#include "rx_common.cuh"
+#include "rx_fused.cuh"
+
+using namespace rfid_b200;
+
+struct rfid_b200_ctx {
+  rfid_b200_params params;
+  RxConfig cfg;
+  int device;
+  cudaStream_t stream;  // own stream for block mode / host-mode capture calls
+  std::string last_error;
+  // capture mode
+  FusedArgs layout;     // shared-memory carve-up (pointers filled per call)
+  float* window_tap;
+  int last_launches;
+  bool timing;
+  cudaEvent_t ev0, ev1;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  float kernel_ms;
+  int kernel_launches;
+  // host-mode staging buffers
+  void* d_iq; size_t d_iq_bytes;
+  void* d_segs; size_t d_segs_bytes;
+  void* d_res; size_t d_res_bytes;
+  void* d_cnt; size_t d_cnt_bytes;
+  // block mode
+  GateState* d_gate;
+  GateCallOut* d_gate_out;
+  void* d_in; size_t d_in_bytes;
+  void* d_out; size_t d_out_bytes;
+  void* d_m2; size_t d_m2_bytes;
+  rfid_b200_window_result* d_one;
+  // mf block mode
+  void* d_mf; size_t d_mf_bytes; long long mf_abs0; long long mf_have; long long mf_next_n;
+};
+
+namespace {
+
+const char* kErrNames[] = {"ok", "invalid argument", "no usable sm_100 CUDA device", "out of memory", "CUDA runtime error",
+                           "output buffer too small"};
+
+int fail_cuda(rfid_b200_ctx* c, cudaError_t e, const char* what)
+{
+  if (c) c->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return RFID_B200_ECUDA;
+}
+#define CK(call)                                                   \
+  do {                                                             \
+    cudaError_t _e = (call);                                       \
+    if (_e != cudaSuccess) return fail_cuda(ctx, _e, #call);       \
+  } while (0)
+
+int next_pow2(int v)
+{
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Derived counts with the reference's own expression order and types
+// (gate_impl.cc:48-53,115,121; tag_decoder_impl.cc:60,85,151-152; global_vars.h:110-111).
+int derive_config(const rfid_b200_params& p, RxConfig& c)
+{
+  if (p.adc_rate <= 0 || p.decim <= 0 || p.ntaps <= 0 || p.fixed_q < 0 || p.fixed_q > 15) return RFID_B200_EINVAL;
+  memset(&c, 0, sizeof(c));
+  c.adc_rate = p.adc_rate; c.decim = p.decim; c.ntaps = p.ntaps;
+  const int sample_rate = p.adc_rate / p.decim;  // apps/reader.py:76
+  c.fs_dec = sample_rate;
+  const float TAG_BIT_D = (float)(1.0 / kReaderFreq * std::pow(10, 6));
+  c.n_T1 = (int)(kT1_D * (sample_rate / std::pow(10, 6)));
+  c.n_PW = (int)(kPW_D * (sample_rate / std::pow(10, 6)));
+  c.n_tag_bit_i = (int)(TAG_BIT_D * (sample_rate / std::pow(10, 6)));
+  c.win_length = (int)(kWinSizeD * (sample_rate / std::pow(10, 6)));
+  c.dc_length = (int)(kDcSizeD * (sample_rate / std::pow(10, 6)));
+  c.n_tag_bit_f = (float)(TAG_BIT_D * sample_rate / std::pow(10, 6));
+  c.len_epc = (kEPCBits + kTagPreambleBits) * c.n_tag_bit_i + 2 * c.n_tag_bit_i;
+  c.len_rn16 = (kRN16Bits + kTagPreambleBits) * c.n_tag_bit_i + 2 * c.n_tag_bit_i;
+  c.fixed_q = p.fixed_q; c.max_queries = p.max_queries; c.max_tags = p.max_tags;
+  c.mf_q = p.ntaps / p.decim; c.mf_rem = p.ntaps % p.decim;
+  int sr = 0;
+  for (int i = 0; i < 1.5 * c.n_tag_bit_f; i++) sr++;  // tag_decoder_impl.cc:85
+  c.sync_range = sr;
+  const float n = c.n_tag_bit_f;
+  c.t_min = (float)(n / 2.0 - n / 2.0 / 100);  // :151
+  c.t_max = (float)(n / 2.0 + n / 2.0 / 100);  // :152
+  if (c.win_length < 1 || c.dc_length < 1 || c.n_tag_bit_i < 1 || c.win_length > kMaxWinLen || c.dc_length > kMaxDcLen)
+    return RFID_B200_EINVAL;
+  return RFID_B200_OK;
+}
+
+int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+void make_layout(const RxConfig& c, FusedArgs& L)
+{
+  int off = 0;
+  L.raw_stage_samples = c.decim * kTT + 2;
+  L.off_raw = off; off = align_up(off + kRawStages * L.raw_stage_samples * 8, 16);
+  L.bhist_size = next_pow2(kTT + c.mf_q + 2);
+  L.off_bhist = off; off = align_up(off + L.bhist_size * 8 * (c.mf_rem ? 2 : 1), 16);
+  L.ahist_size = next_pow2(kTT + c.win_length);
+  L.off_ahist = off; off = align_up(off + L.ahist_size * 4, 16);
+  L.off_tile_y = off; off += kTileStages * kTT * 8;
+  L.off_tile_a = off; off += kTileStages * kTT * 4;
+  L.off_tile_d = off; off += kTileStages * kTT * 4;
+  L.ycl_size = next_pow2(kTT + c.dc_length);
+  L.off_ycl = off; off = align_up(off + L.ycl_size * 8, 16);
+  L.off_e = off; off += 2 * kTT * 4;
+  L.off_win = off; off = align_up(off + c.len_epc * 8, 16);
+  L.off_M = off; off = align_up(off + c.len_epc * 4, 16);
+  L.smem_bytes = off;
+}
+
+typedef void (*fused_fn)(const FusedArgs);
+fused_fn pick_kernel(int decim)
+{
+  switch (decim) {
+    case 5: return rx_fused_kernel<5>;
+    default: return nullptr;
+  }
+}
+
+int grow(rfid_b200_ctx* ctx, void** p, size_t* have, size_t need)
+{
+  if (*have >= need) return RFID_B200_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  size_t want = need + need / 4 + 256;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) { ctx->last_error = "cudaMalloc failed"; cudaGetLastError(); return RFID_B200_ENOMEM; }
+  *have = want;
+  return RFID_B200_OK;
+}
+
+void drain_timing(rfid_b200_ctx* ctx)
+{
+  for (auto& pr : ctx->pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      ctx->kernel_ms += ms;
+      ctx->kernel_launches++;
+    }
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  ctx->pending.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+int rfid_b200_abi_version(void) { return RFID_B200_ABI_VERSION; }
+
+const char* rfid_b200_strerror(int code)
+{
+  int k = -code;
+  if (k < 0 || k > 5) return "unknown error";
+  return kErrNames[k];
+}
+
+const char* rfid_b200_last_cuda_error(const rfid_b200_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+void rfid_b200_default_params(rfid_b200_params* p)
+{
+  if (!p) return;
+  p->adc_rate = 2000000;  // apps/reader.py:53
+  p->decim = 5;           // apps/reader.py:54
+  p->ntaps = 25;          // apps/reader.py:65
+  p->fixed_q = 0;         // global_vars.h:72
+  p->max_queries = 1000;  // global_vars.h:76
+  p->max_tags = 100;      // global_vars.h:100
+  p->device = 0;
+  p->reserved = 0;
+}
+
+int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
+{
+  if (!p || !out) return RFID_B200_EINVAL;
+  *out = nullptr;
+  RxConfig cfg;
+  int rc = derive_config(*p, cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || p->device < 0 || p->device >= ndev) { cudaGetLastError(); return RFID_B200_ENODEV; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major != 10) { cudaGetLastError(); return RFID_B200_ENODEV; }
+  rfid_b200_ctx* ctx = new (std::nothrow) rfid_b200_ctx();
+  if (!ctx) return RFID_B200_ENOMEM;
+  ctx->params = *p; ctx->cfg = cfg; ctx->device = p->device;
+  ctx->window_tap = nullptr; ctx->last_launches = 0; ctx->timing = false; ctx->kernel_ms = 0.f; ctx->kernel_launches = 0;
+  ctx->d_iq = ctx->d_segs = ctx->d_res = ctx->d_cnt = ctx->d_in = ctx->d_out = ctx->d_m2 = ctx->d_mf = nullptr;
+  ctx->d_iq_bytes = ctx->d_segs_bytes = ctx->d_res_bytes = ctx->d_cnt_bytes = ctx->d_in_bytes = ctx->d_out_bytes = ctx->d_m2_bytes = ctx->d_mf_bytes = 0;
+  ctx->d_gate = nullptr; ctx->d_gate_out = nullptr; ctx->d_one = nullptr;
+  ctx->mf_abs0 = 0; ctx->mf_have = 0; ctx->mf_next_n = 0;
+  memset(&ctx->layout, 0, sizeof(ctx->layout));
+  make_layout(cfg, ctx->layout);
+  cudaError_t e = cudaSetDevice(p->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_gate, sizeof(GateState));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_gate_out, sizeof(GateCallOut));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_one, sizeof(rfid_b200_window_result));
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_gate, 0, sizeof(GateState), ctx->stream);
+  if (e == cudaSuccess) {
+    // gate_impl ctor (gate_impl.cc:45) + initialize_reader_state (global_vars.cc:47): NEG_EDGE, first SEEK = RN16
+    GateState init;
+    memset(&init, 0, sizeof(init));
+    init.to_ungate = cfg.len_rn16;
+    e = cudaMemcpyAsync(ctx->d_gate, &init, offsetof(GateState, win_samples), cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  fused_fn fn = pick_kernel(cfg.decim);
+  if (e == cudaSuccess && fn)
+    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->layout.smem_bytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute((const void*)decode_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             cfg.len_epc * 12 + 64);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    rfid_b200_destroy(ctx);
+    return RFID_B200_ECUDA;
+  }
+  *out = ctx;
+  return RFID_B200_OK;
+}
+
+void rfid_b200_destroy(rfid_b200_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  drain_timing(ctx);
+  void* ptrs[] = {ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
+                  ctx->d_gate, ctx->d_gate_out, ctx->d_one};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int rfid_b200_window_length(const rfid_b200_ctx* ctx, int kind)
+{
+  if (!ctx) return RFID_B200_EINVAL;
+  return kind == RFID_B200_RN16 ? ctx->cfg.len_rn16 : ctx->cfg.len_epc;
+}
+
+int rfid_b200_fs_dec(const rfid_b200_ctx* ctx) { return ctx ? ctx->cfg.fs_dec : RFID_B200_EINVAL; }
+
+int rfid_b200_set_window_tap(rfid_b200_ctx* ctx, float* d_windows)
+{
+  if (!ctx) return RFID_B200_EINVAL;
+  ctx->window_tap = d_windows;
+  return RFID_B200_OK;
+}
+
+int rfid_b200_enable_kernel_timing(rfid_b200_ctx* ctx, int on)
+{
+  if (!ctx) return RFID_B200_EINVAL;
+  ctx->timing = on != 0;
+  return RFID_B200_OK;
+}
+
+int rfid_b200_kernel_time(rfid_b200_ctx* ctx, int reset, float* ms_total, int* launches)
+{
+  if (!ctx) return RFID_B200_EINVAL;
+  cudaSetDevice(ctx->device);
+  drain_timing(ctx);
+  if (ms_total) *ms_total = ctx->kernel_ms;
+  if (launches) *launches = ctx->kernel_launches;
+  if (reset) { ctx->kernel_ms = 0.f; ctx->kernel_launches = 0; }
+  return RFID_B200_OK;
+}
+
+int rfid_b200_last_launch_count(const rfid_b200_ctx* ctx) { return ctx ? ctx->last_launches : RFID_B200_EINVAL; }
+
+int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw, const rfid_b200_segment* d_segs, int nseg,
+                             int max_windows_per_segment, rfid_b200_window_result* d_results, int32_t* d_counts,
+                             void* stream)
+{
+  if (!ctx || !d_iq || !d_segs || !d_results || !d_counts || nseg < 0 || max_windows_per_segment < 1) return RFID_B200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(d_iq) & 15u) != 0) return RFID_B200_EINVAL;  // TMA bulk source alignment
+  ctx->last_launches = 0;
+  if (nseg == 0) return RFID_B200_OK;
+  fused_fn fn = pick_kernel(ctx->cfg.decim);
+  if (!fn) { ctx->last_error = "capture mode supports decim = 5 only in this build"; return RFID_B200_EINVAL; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  FusedArgs A = ctx->layout;
+  A.iq = reinterpret_cast<const float2*>(d_iq);
+  A.n_raw = n_raw;
+  A.segs = d_segs;
+  A.nseg = nseg;
+  A.max_windows = max_windows_per_segment;
+  A.results = d_results;
+  A.counts = d_counts;
+  A.window_tap = reinterpret_cast<float2*>(ctx->window_tap);
+  A.cfg = ctx->cfg;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, s));
+  }
+  fn<<<nseg, kFusedThreads, A.smem_bytes, s>>>(A);
+  CK(cudaGetLastError());
+  if (ctx->timing) {
+    CK(cudaEventRecord(e1, s));
+    ctx->pending.emplace_back(e0, e1);
+  }
+  ctx->last_launches = 1;
+  return RFID_B200_OK;
+}
+
+int rfid_b200_decode_capture_host(rfid_b200_ctx* ctx, const float* h_iq, size_t n_raw, const rfid_b200_segment* h_segs,
+                                  int nseg, int max_windows_per_segment, rfid_b200_window_result* h_results,
+                                  int32_t* h_counts)
+{
+  if (!ctx || !h_iq || !h_segs || !h_results || !h_counts || nseg < 0 || max_windows_per_segment < 1) return RFID_B200_EINVAL;
+  if (nseg == 0) return RFID_B200_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  const size_t res_bytes = (size_t)nseg * max_windows_per_segment * sizeof(rfid_b200_window_result);
+  if ((rc = grow(ctx, &ctx->d_iq, &ctx->d_iq_bytes, n_raw * 8 + 16))) return rc;
+  if ((rc = grow(ctx, &ctx->d_segs, &ctx->d_segs_bytes, (size_t)nseg * sizeof(rfid_b200_segment)))) return rc;
+  if ((rc = grow(ctx, &ctx->d_res, &ctx->d_res_bytes, res_bytes))) return rc;
+  if ((rc = grow(ctx, &ctx->d_cnt, &ctx->d_cnt_bytes, (size_t)nseg * 4))) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->d_iq, h_iq, n_raw * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->d_segs, h_segs, (size_t)nseg * sizeof(rfid_b200_segment), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ctx->d_res, 0, res_bytes, s));
+  rc = rfid_b200_decode_capture(ctx, (const float*)ctx->d_iq, n_raw, (const rfid_b200_segment*)ctx->d_segs, nseg,
+                                max_windows_per_segment, (rfid_b200_window_result*)ctx->d_res, (int32_t*)ctx->d_cnt, s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_results, ctx->d_res, res_bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_counts, ctx->d_cnt, (size_t)nseg * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return RFID_B200_OK;
+}
+
+// READER_STATS bookkeeping: tag_decoder_impl.cc:269-288 (RN16 too short), :295 (slot++ per EPC window),
+// :329-365 (CRC ok), :366-387 (CRC fail), reader_impl.cc:259,336 (n_queries_sent), gate_impl.cc:101-109 (stop rule).
+int rfid_b200_reduce_stats(const rfid_b200_ctx* ctx, const rfid_b200_window_result* recs, const int32_t* counts, int nseg,
+                           int max_per_seg, int continuous, rfid_b200_stats* out)
+{
+  if (!ctx || !recs || !counts || !out || nseg < 0 || max_per_seg < 1) return RFID_B200_EINVAL;
+  memset(out, 0, sizeof(*out));
+  const int max_slot = 1 << ctx->cfg.fixed_q;
+  out->max_slot_number = max_slot;
+  std::map<int, int> tag_reads;
+  int round = 1, slot = 1, nq = 1, total_q = 0;
+  bool stopped = false;
+  for (int s = 0; s < nseg; s++) {
+    if (!continuous) { round = 1; slot = 1; nq = 1; stopped = false; }
+    const int n = counts[s] < max_per_seg ? counts[s] : max_per_seg;
+    const rfid_b200_window_result* r = recs + (size_t)s * max_per_seg;
+    for (int k = 0; k < n && !stopped; k++) {
+      bool next_query = false;
+      if (r[k].kind == RFID_B200_RN16) {
+        if (r[k].crc_ok == -2) {
+          slot++;
+          if (slot > max_slot) { slot = 1; round++; }
+          next_query = true;
+        }
+      } else {
+        slot++;
+        if (slot > max_slot) { slot = 1; round++; }
+        if (r[k].crc_ok == 1) { out->n_epc_correct++; tag_reads[r[k].tag_id]++; }
+        next_query = true;
+      }
+      out->n_windows++;
+      if (next_query) {
+        nq++;
+        if (nq > ctx->cfg.max_queries || (int)tag_reads.size() > ctx->cfg.max_tags) stopped = true;
+      }
+    }
+    if (!continuous) total_q += nq;
+  }
+  out->n_queries_sent = continuous ? nq : total_q;
+  out->cur_inventory_round = round;
+  out->cur_slot_number = slot;
+  out->terminated = stopped ? 1 : 0;
+  out->n_unique_tags = (int)tag_reads.size();
+  int k = 0;
+  for (auto& kv : tag_reads) {
+    if (k >= RFID_B200_MAX_TAGS) break;
+    out->tag_id[k] = kv.first;
+    out->tag_reads[k] = kv.second;
+    k++;
+  }
+  return RFID_B200_OK;
+}
+
+// ------------------------------------------------------------------ block mode
+int rfid_b200_gate_work(rfid_b200_ctx* ctx, int seek, const float* in, int n_in, float* out, int out_capacity,
+                        int* consumed, int* written, int* closed, float* magn2_out)
+{
+  if (!ctx || !in || !out || !consumed || !written || n_in < 0 || seek < 0 || seek > 2) return RFID_B200_EINVAL;
+  if (out_capacity < n_in) return RFID_B200_ECAPACITY;  // the reference may write up to ninput items (gate_impl.cc:95,174,187)
+  *consumed = 0; *written = 0;
+  if (closed) *closed = 0;
+  if (n_in == 0 && seek == 0) return RFID_B200_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  const size_t bytes = (size_t)(n_in > 0 ? n_in : 1) * 8;
+  if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_bytes, bytes))) return rc;
+  if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_bytes, bytes))) return rc;
+  if ((rc = grow(ctx, &ctx->d_m2, &ctx->d_m2_bytes, bytes / 2))) return rc;
+  cudaStream_t s = ctx->stream;
+  if (n_in) CK(cudaMemcpyAsync(ctx->d_in, in, (size_t)n_in * 8, cudaMemcpyHostToDevice, s));
+  gate_block_kernel<<<1, 32, 0, s>>>(ctx->cfg, ctx->d_gate, seek, (const float2*)ctx->d_in, n_in, (float2*)ctx->d_out,
+                                     (float*)ctx->d_m2, ctx->d_gate_out);
+  CK(cudaGetLastError());
+  GateCallOut r;
+  CK(cudaMemcpyAsync(&r, ctx->d_gate_out, sizeof(r), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (r.written > 0) {
+    CK(cudaMemcpyAsync(out, ctx->d_out, (size_t)r.written * 8, cudaMemcpyDeviceToHost, s));
+    if (magn2_out) CK(cudaMemcpyAsync(magn2_out, ctx->d_m2, (size_t)r.written * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  *consumed = r.consumed; *written = r.written;
+  if (closed) *closed = r.closed;
+  ctx->last_launches = 1;
+  return RFID_B200_OK;
+}
+
+int rfid_b200_decoder_work(rfid_b200_ctx* ctx, int kind, const float* win, int n, rfid_b200_window_result* res,
+                           float* bits_out)
+{
+  if (!ctx || !win || !res || (kind != RFID_B200_RN16 && kind != RFID_B200_EPC)) return RFID_B200_EINVAL;
+  const int need = kind == RFID_B200_RN16 ? ctx->cfg.len_rn16 : ctx->cfg.len_epc;
+  if (n < need) return RFID_B200_EINVAL;  // the reference only fires on a complete window (tag_decoder_impl.cc:223,291)
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_bytes, (size_t)need * 8))) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->d_in, win, (size_t)need * 8, cudaMemcpyHostToDevice, s));
+  decode_block_kernel<<<1, 32, (size_t)need * 12 + 64, s>>>(ctx->cfg, kind, (const float2*)ctx->d_in, need, ctx->d_one);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(res, ctx->d_one, sizeof(*res), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (bits_out) {
+    const int nb = kind == RFID_B200_RN16 ? 16 : 128;
+    for (int i = 0; i < nb; i++) bits_out[i] = (res->bits[i >> 3] >> (7 - (i & 7))) & 1 ? 1.0f : 0.0f;
+  }
+  ctx->last_launches = 1;
+  return RFID_B200_OK;
+}
+
+int rfid_b200_mf_work(rfid_b200_ctx* ctx, const float* in, int n_in, float* out, int out_capacity, int* written)
+{
+  if (!ctx || !in || !out || !written || n_in < 0) return RFID_B200_EINVAL;
+  *written = 0;
+  CK(cudaSetDevice(ctx->device));
+  const int D = ctx->cfg.decim, K = ctx->cfg.ntaps;
+  const long long abs_end = ctx->mf_abs0 + ctx->mf_have + n_in;       // one past the newest sample
+  const long long last_n = abs_end / D - 1;  // floor(total/decim) outputs exist so far (fixed-rate decimator)
+  const long long n_out = last_n - ctx->mf_next_n + 1 > 0 ? last_n - ctx->mf_next_n + 1 : 0;
+  if (n_out > out_capacity) return RFID_B200_ECAPACITY;
+  int rc;
+  const size_t total = (size_t)(ctx->mf_have + n_in);
+  void* nbuf = nullptr; size_t nbytes = 0;
+  // staging buffer = carried history + new chunk
+  if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_bytes, (total + 1) * 8))) return rc;
+  (void)nbuf; (void)nbytes;
+  cudaStream_t s = ctx->stream;
+  if (ctx->mf_have) CK(cudaMemcpyAsync(ctx->d_out, ctx->d_mf, (size_t)ctx->mf_have * 8, cudaMemcpyDeviceToDevice, s));
+  if (n_in) CK(cudaMemcpyAsync((char*)ctx->d_out + (size_t)ctx->mf_have * 8, in, (size_t)n_in * 8, cudaMemcpyHostToDevice, s));
+  if (n_out > 0) {
+    if ((rc = grow(ctx, &ctx->d_m2, &ctx->d_m2_bytes, (size_t)n_out * 8))) return rc;
+    const int threads = 128;
+    mf_block_kernel<<<(unsigned)((n_out + threads - 1) / threads), threads, 0, s>>>(
+        ctx->cfg, (const float2*)ctx->d_out, ctx->mf_abs0, ctx->mf_next_n, (int)n_out, (float2*)ctx->d_m2);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_m2, (size_t)n_out * 8, cudaMemcpyDeviceToHost, s));
+  }
+  // keep what the next output still needs: samples from D*next_n - (K-1) on
+  const long long next_n = ctx->mf_next_n + n_out;
+  long long keep_from = (long long)D * next_n - (K - 1);
+  if (keep_from < ctx->mf_abs0) keep_from = ctx->mf_abs0;
+  if (keep_from > abs_end) keep_from = abs_end;
+  const long long keep = abs_end - keep_from;
+  if ((rc = grow(ctx, &ctx->d_mf, &ctx->d_mf_bytes, (size_t)(keep + 1) * 8))) return rc;
+  if (keep) CK(cudaMemcpyAsync(ctx->d_mf, (char*)ctx->d_out + (size_t)(keep_from - ctx->mf_abs0) * 8, (size_t)keep * 8,
+                               cudaMemcpyDeviceToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  ctx->mf_abs0 = keep_from; ctx->mf_have = keep; ctx->mf_next_n = next_n;
+  *written = (int)n_out;
+  ctx->last_launches = n_out > 0 ? 1 : 0;
+  return RFID_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// rx_common.cuh -- shared definitions of the sm_100a Gen2 receive path:
+// derived configuration, the numerical contract (how each libm/libgcc call the
+// reference makes is evaluated on the device), mbarrier / TMA-bulk PTX wrappers.
+//
+// Numerical contract (every item is exercised by the
+// parity tests against the compiled reference):
+//   * no FMA contraction anywhere: this translation unit is built with
+//     -fmad=false and all arithmetic that must round like the reference uses
+//     the explicit _rn intrinsics;
+//   * std::abs(complex<float>) = glibc cabsf = (float)sqrt((double)re*re + (double)im*im)
+//     (gate_impl.cc:130);
+//   * z / complex<float>(N,0) = one IEEE float division per component
+//     (libgcc __divsc3 with a zero imaginary divisor; gate_impl.cc:141, tag_decoder_impl.cc:103);
+//   * std::norm = re*re + im*im with three roundings (libstdc++ 13);
+//   * complex * complex = (ac - bd, ad + bc) with separately rounded products.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rfid_b200.h"
+
+namespace rfid_b200 {
+
+// ---- protocol constants: include/rfid/global_vars.h:72-143 of the reference ----
+constexpr int kT1_D = 240;                // us
+constexpr int kPW_D = 12;                 // us
+constexpr int kNumPulsesCommand = 5;
+constexpr int kTagPreambleBits = 6;
+constexpr int kRN16Bits = 17;
+constexpr int kEPCBits = 129;
+constexpr int kWinSizeD = 250;            // us
+constexpr int kDcSizeD = 120;             // us
+constexpr int kReaderFreq = 40000;        // BLF
+constexpr float kThreshFraction = 0.75f;
+constexpr unsigned kPreambleMask = 0xC4B; // TAG_PREAMBLE {1,1,0,1,0,0,1,0,0,0,1,1}: bit j = P[j]
+
+// Derived sample counts (gate_impl.cc:48-53,115,121; tag_decoder_impl.cc:60), computed on the
+// host with the reference's own double/float expression order.
+struct RxConfig {
+  int adc_rate, decim, ntaps;
+  int fs_dec;
+  int n_T1, n_PW, n_tag_bit_i;
+  float n_tag_bit_f;
+  int win_length, dc_length;
+  int len_rn16, len_epc;
+  int fixed_q, max_queries, max_tags;
+  int mf_q, mf_rem;        // ntaps / decim, ntaps % decim
+  int sync_range;          // number of i with i < 1.5 * n_tag_bit_f   (tag_decoder_impl.cc:85)
+  float t_min, t_max;      // EPC period search bounds (tag_decoder_impl.cc:151-152)
+};
+
+// ---------------------------------------------------------------- arithmetic primitives
+__device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// glibc cabsf(re + i*im): products are exact in double, one rounding for the sum, correctly
+// rounded double sqrt, one rounding to float.
+__device__ __forceinline__ float cabsf_ref(float re, float im)
+{
+  double dr = (double)re, di = (double)im;
+  double s = __fma_rn(di, di, __dmul_rn(dr, dr));  // dr*dr exact (48 bits) => fma == round(dr*dr + di*di)
+  return __double2float_rn(__dsqrt_rn(s));
+}
+
+__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return make_float2(f_add(a.x, b.x), f_add(a.y, b.y)); }
+__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return make_float2(f_sub(a.x, b.x), f_sub(a.y, b.y)); }
+__device__ __forceinline__ float c_norm(float2 a) { return f_add(f_mul(a.x, a.x), f_mul(a.y, a.y)); }
+// std::real((a - b) * std::conj(h)): (x+iy)(c+id) with d = -h.y, real = x*c - y*d
+__device__ __forceinline__ float c_proj(float2 a, float2 b, float2 h)
+{
+  float x = f_sub(a.x, b.x), y = f_sub(a.y, b.y);
+  return f_sub(f_mul(x, h.x), f_mul(y, -h.y));
+}
+
+// ---------------------------------------------------------------- mbarrier / TMA (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar`
+// (SASS: UBLKCP).  dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace rfid_b200

@@ -1,0 +1,208 @@
+// rx_decode.cuh -- one warp decodes one ungated window held in shared memory.
+// Replaces tag_decoder_impl::general_work and its helpers
+// (reference gr-rfid/lib/tag_decoder_impl.cc:78-193, 223-393, 401-445).
+#pragma once
+
+#include "rx_common.cuh"
+
+namespace rfid_b200 {
+
+struct WindowDecode {
+  int sync_index;
+  float score;
+  float2 h;
+  float T;
+  int crc_ok;
+  int tag_id;
+  uint32_t bits[4];  // bit j of the message at word j/32, bit position 31 - j%32 (MSB first)
+};
+
+// warp argmax with the reference's tie rule: first (lowest index) strict maximum
+__device__ __forceinline__ void warp_argmax_first(float& v, int& idx)
+{
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, off);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    bool take = (ov > v) || (ov == v && oi < idx);
+    v = take ? ov : v;
+    idx = take ? oi : idx;
+  }
+}
+
+// CRC-16/CCITT over the first 14 bytes, bitwise like check_crc (tag_decoder_impl.cc:424-440)
+__device__ __forceinline__ int crc16_check(const uint32_t bits[4])
+{
+  unsigned crc = 0xFFFF;
+#pragma unroll 1
+  for (int i = 0; i < 14; i++) {
+    unsigned byte = (bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
+    crc ^= byte << 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) crc = (crc & 0x8000u) ? (((crc << 1) ^ 0x1021u) & 0xFFFFu) : ((crc << 1) & 0xFFFFu);
+  }
+  crc = (~crc) & 0xFFFFu;
+  unsigned rcvd = bits[3] & 0xFFFFu;  // bytes 14,15
+  return rcvd == crc ? 1 : 0;
+}
+
+// w: window samples (y - dc_est), n_avail samples; M: scratch for |w|^2 (EPC only, >= n_avail floats).
+// All 32 lanes of the warp must call; the result is valid in every lane.
+__device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, const float2* __restrict__ w,
+                                                   int n_avail, float* __restrict__ M, WindowDecode& out)
+{
+  const int lane = threadIdx.x & 31;
+  const float n = c.n_tag_bit_f;
+
+  // ---- tag_sync (tag_decoder_impl.cc:85-100): sync_range offsets x 12 taps, first strict max from 0
+  float best = -1.0f;
+  int best_i = 0x7fffffff;
+  for (int i = lane; i < c.sync_range; i += 32) {
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int j = 0; j < 2 * kTagPreambleBits; j++) {
+      int k = (int)f_add((float)i, f_div(f_mul((float)j, n), 2.0f));  // (int)(i + j*n/2), :92
+      float2 s = w[k];
+      float cr = (float)((kPreambleMask >> j) & 1u);
+      // in[k] * gr_complex(P[j], 0)  ->  (a*c - b*0, a*0 + b*c)
+      float pr = f_sub(f_mul(s.x, cr), f_mul(s.y, 0.0f));
+      float pi = f_add(f_mul(s.x, 0.0f), f_mul(s.y, cr));
+      acc.x = f_add(acc.x, pr);
+      acc.y = f_add(acc.y, pi);
+    }
+    float corr = c_norm(acc);
+    if (corr > best) {  // per-lane candidates ascend in i, so strict > keeps the first
+      best = corr;
+      best_i = i;
+    }
+  }
+  warp_argmax_first(best, best_i);
+  int max_index = 0;
+  float max_corr = 0.0f;
+  if (best > 0.0f) {  // `if (corr > max)` with max initialised to 0 (:81,95)
+    max_index = best_i;
+    max_corr = best;
+  }
+  // ---- h_est (:103)
+  {
+    int t1 = (int)f_add((float)max_index, f_div(n, 2.0f));
+    int t3 = (int)f_add((float)max_index, f_div(f_mul(3.0f, n), 2.0f));
+    int t6 = (int)f_add((float)max_index, f_div(f_mul(6.0f, n), 2.0f));
+    int t10 = (int)f_add((float)max_index, f_div(f_mul(10.0f, n), 2.0f));
+    int t11 = (int)f_add((float)max_index, f_div(f_mul(11.0f, n), 2.0f));
+    float2 s = w[max_index];
+    s = c_add(s, w[t1]);
+    s = c_add(s, w[t3]);
+    s = c_add(s, w[t6]);
+    s = c_add(s, w[t10]);
+    s = c_add(s, w[t11]);
+    out.h = make_float2(f_div(s.x, 6.0f), f_div(s.y, 6.0f));
+  }
+  out.sync_index = max_index;
+  out.score = max_corr;
+  // :107  max_index + TAG_PREAMBLE_BITS * n + n/2, truncated
+  const int index = (int)f_add(f_add((float)max_index, f_mul((float)kTagPreambleBits, n)), f_div(n, 2.0f));
+  const float2 h = out.h;
+  out.bits[0] = out.bits[1] = out.bits[2] = out.bits[3] = 0u;
+
+  if (kind == RFID_B200_RN16) {
+    // ---- half-bit sampling (:237-253): j_m = index + m*(n/2) accumulated in float (exact here)
+    const float half = f_div(n, 2.0f);
+    const int want = 2 * (kRN16Bits - 1);  // 32 samples
+    float jm = (float)index;
+    for (int m = 0; m < lane; m++) jm = f_add(jm, half);
+    bool have = jm < (float)n_avail;
+    unsigned have_mask = __ballot_sync(0xffffffffu, have);
+    float2 s = make_float2(0.0f, 0.0f);
+    if (have) s = w[(int)roundf(jm)];
+    out.T = 0.0f;
+    out.crc_ok = -1;
+    if (have_mask == 0xffffffffu && want == 32) {
+      // ---- tag_detection_RN16 (:121-140)
+      float2 s_next = make_float2(__shfl_down_sync(0xffffffffu, s.x, 1), __shfl_down_sync(0xffffffffu, s.y, 1));
+      float res = c_proj(s, s_next, h);
+      unsigned pos = __ballot_sync(0xffffffffu, res > 0.0f);
+      // keep even lanes (pair j = lanes 2j, 2j+1), compact to 16 sign bits
+      unsigned S = 0;
+#pragma unroll
+      for (int j = 0; j < 16; j++) S |= ((pos >> (2 * j)) & 1u) << j;
+      // bit_j = (sign_j != sign_{j-1}), sign_{-1} = positive
+      unsigned B = (S ^ ((S << 1) | 1u)) & 0xFFFFu;
+      unsigned msb = 0;
+#pragma unroll
+      for (int j = 0; j < 16; j++) msb |= ((B >> j) & 1u) << (31 - j);
+      out.bits[0] = msb;
+      out.tag_id = (int)(msb >> 16);
+    } else {
+      out.crc_ok = -2;  // window too short for 32 half bits: the branch at :269-288
+      out.tag_id = -1;
+    }
+    return;
+  }
+
+  // ---- EPC: magn_squared_samples (gate_impl.cc:172,186)
+  for (int p = lane; p < n_avail; p += 32) M[p] = c_norm(w[p]);
+  __syncwarp();
+  // ---- symbol-period search (:151-165): 20 candidates, 256 sequential gathers each
+  const int number_steps = 20;
+  const float min_val = c.t_min, max_val = c.t_max;
+  float energy = -1.0f;
+  int e_idx = 0x7fffffff;
+  if (lane < number_steps) {
+    const float Tt = f_add(min_val, f_div(f_mul((float)lane, f_sub(max_val, min_val)), (float)(number_steps - 1)));
+    float e = 0.0f;
+#pragma unroll 4
+    for (int i = 0; i < 256; i++) {
+      int p = (int)f_add(f_mul((float)i, Tt), (float)index);  // :161
+      e = f_add(e, M[p]);
+    }
+    energy = e;
+    e_idx = lane;
+  }
+  // std::max_element: first largest (NaN never wins a `<` comparison; energies here are finite)
+  warp_argmax_first(energy, e_idx);
+  const int index_T = e_idx;
+  const float T = f_add(min_val, f_div(f_mul((float)index_T, f_sub(max_val, min_val)), (float)(number_steps - 1)));  // :166
+  out.T = T;
+  // ---- 128 bit decisions (:171-191)
+  const float twoT = f_mul(2.0f, T);
+  unsigned S[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    int j = r * 32 + lane;
+    int a = (int)f_add(f_mul((float)j, twoT), (float)index);                       // j*(2*T) + index
+    int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);          // j*2*T + T + index
+    float res = c_proj(w[a], w[b], h);
+    S[r] = __ballot_sync(0xffffffffu, res > 0.0f);  // bit lane = sign of pair j
+  }
+  // bit_j = sign_j ^ sign_{j-1}, sign_{-1} = 1
+  unsigned carry = 1u;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    unsigned prev = (S[r] << 1) | carry;
+    carry = S[r] >> 31;
+    unsigned B = S[r] ^ prev;                 // bit lane = message bit 32r + lane
+    out.bits[r] = __brev(B);                  // MSB first
+  }
+  out.crc_ok = crc16_check(out.bits);
+  out.tag_id = (int)((out.bits[3] >> 16) & 0xFFu);  // byte 13 = bits[104..111] (:348-352)
+}
+
+__device__ __forceinline__ void store_result(rfid_b200_window_result* dst, const WindowDecode& d, int segment, int window,
+                                             int open_index, int length, int kind)
+{
+  // one lane writes the 64-byte record as four 16-byte stores
+  int4 q0 = make_int4(segment, window, open_index, length);
+  int4 q1 = make_int4(kind, d.sync_index, __float_as_int(d.score), __float_as_int(d.h.x));
+  int4 q2 = make_int4(__float_as_int(d.h.y), __float_as_int(d.T), d.crc_ok, d.tag_id);
+  // bits[]: byte k = message bits 8k..8k+7, MSB first => big-endian words
+  int4 q3 = make_int4((int)__byte_perm(d.bits[0], 0, 0x0123), (int)__byte_perm(d.bits[1], 0, 0x0123),
+                      (int)__byte_perm(d.bits[2], 0, 0x0123), (int)__byte_perm(d.bits[3], 0, 0x0123));
+  int4* p = reinterpret_cast<int4*>(dst);
+  p[0] = q0;
+  p[1] = q1;
+  p[2] = q2;
+  p[3] = q3;
+}
+
+}  // namespace rfid_b200

@@ -53,6 +53,13 @@ size_t gen2_oracle_mf(const float* x, size_t n_in, int ntaps, int decim, float* 
   return oracle_mf_boxcar(x, n_in, ntaps, decim, y);
 }
 
+size_t gen2_oracle_mf_variant(const float* x, size_t n_in, int ntaps, int decim, float* y, int variant)
+{
+  /* variant 0: canonical; 1: sequential ascending float32; 2: float64 accumulation */
+  if (variant == 0) return oracle_mf_boxcar(x, n_in, ntaps, decim, y);
+  return oracle_mf_boxcar_sequential(x, n_in, ntaps, decim, y, variant == 2);
+}
+
 /* std::abs(std::complex<float>) -> cabsf (gate_impl.cc:130) */
 float gen2_oracle_cabsf(float re, float im)
 {

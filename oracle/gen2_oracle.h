@@ -71,6 +71,7 @@ GEN2_ORACLE_API int gen2_oracle_decode_segments(const gen2_oracle_cfg* c, const 
                                                 double* seconds);
 
 GEN2_ORACLE_API size_t gen2_oracle_mf(const float* x, size_t n_in, int ntaps, int decim, float* y);
+GEN2_ORACLE_API size_t gen2_oracle_mf_variant(const float* x, size_t n_in, int ntaps, int decim, float* y, int variant);
 
 /* READER_STATS bookkeeping (tag_decoder_impl.cc:269-288,295,329-387; reader_impl.cc:251-344;
  * stop rule gate_impl.cc:101-109) replayed over records in stream order. */

@@ -6,14 +6,24 @@
  * is NOT under /root/reference and its float summation order depends on the
  * SIMD kernel VOLK selects at run time.  No reference test pins that order, so
  * at the bit level this stage is "parity unpinned" and the build DEFINES the
- * canonical order here:
+ * canonical order here -- the polyphase "integrate-and-dump, then moving sum"
+ * structure of a decimating boxcar (D = decimation, K = ntaps, q = K / D,
+ * rem = K % D, x[<0] = +0.0f, no leading zero terms):
  *
- *   y[n] = ((..((0 + x[D*n-(K-1)]) + x[D*n-(K-2)]) + ...) + x[D*n]),   x[<0] = +0
+ *   B(m) = (((x[D*m-D+1] + x[D*m-D+2]) + ...) + x[D*m])          one block of D raw samples
+ *   P(m) = ((x[D*m-rem+1] + ...) + x[D*m])                        newest `rem` samples of block m
+ *   y[n] = (((P(n-q) + B(n-q+1)) + B(n-q+2)) + ...) + B(n)        (P term only if rem > 0)
  *
- * i.e. one float accumulator per component, starting from +0, input index
- * ascending (the same direction GNU Radio's fir_filter walks its reversed-tap
- * dot product), taps all exactly 1.0 so the products are exact.  Output count is
- * floor(n_in / D) (an output needs its newest sample x[D*n] to exist).
+ * i.e. float32 adds, one accumulator per component, ascending input index
+ * inside a block and ascending blocks (GNU Radio's fir_filter also walks its
+ * reversed-tap dot product in ascending input order; VOLK's SIMD kernels then
+ * split it over 2/4/8 strided accumulators, so no order is "the" reference
+ * order).  Taps are exactly 1.0, so the products are exact.  For the reference
+ * configuration (D = 5, K = 25): five block sums of five samples each.
+ * tests/test_oracle.py checks that the decoded bits, sync indices and T on
+ * misc/data/file_source_test do not depend on this choice (sequential float,
+ * blocked float and float64 accumulation give identical decode results).
+ * Output count is floor(n_in / D) (an output needs its newest sample x[D*n]).
  */
 #ifndef ORACLE_MF_CANONICAL_H
 #define ORACLE_MF_CANONICAL_H
@@ -25,20 +35,58 @@ extern "C" {
 
 /* x: interleaved I,Q float32, n_in complex samples. y: interleaved, capacity n_in/decim.
  * returns number of outputs written. */
+static inline void oracle_mf_partial(const float* x, long lo, long hi, float* sr, float* si)
+{
+  /* ((x[lo] + x[lo+1]) + ...) + x[hi], indices < 0 read as +0 */
+  float ar = 0.0f, ai = 0.0f;
+  for (long k = lo; k <= hi; k++) {
+    float xr = 0.0f, xi = 0.0f;
+    if (k >= 0) { xr = x[2 * k]; xi = x[2 * k + 1]; }
+    if (k == lo) { ar = xr; ai = xi; }
+    else { ar = ar + xr; ai = ai + xi; }
+  }
+  *sr = ar; *si = ai;
+}
+
 static inline size_t oracle_mf_boxcar(const float* x, size_t n_in, int ntaps, int decim, float* y)
+{
+  const long D = decim, q = ntaps / decim, rem = ntaps % decim;
+  size_t n_out = n_in / (size_t)decim;
+  for (size_t n = 0; n < n_out; n++) {
+    float ar = 0.0f, ai = 0.0f, br, bi;
+    int first = 1;
+    long nn = (long)n;
+    if (rem > 0) {
+      oracle_mf_partial(x, D * (nn - q) - rem + 1, D * (nn - q), &ar, &ai);
+      first = 0;
+    }
+    for (long m = nn - q + 1; m <= nn; m++) {
+      oracle_mf_partial(x, D * m - D + 1, D * m, &br, &bi);
+      if (first) { ar = br; ai = bi; first = 0; }
+      else { ar = ar + br; ai = ai + bi; }
+    }
+    y[2 * n] = ar;
+    y[2 * n + 1] = ai;
+  }
+  return n_out;
+}
+
+/* plain sequential-ascending and float64 variants, used only to show that the decode result
+ * does not depend on the summation order */
+static inline size_t oracle_mf_boxcar_sequential(const float* x, size_t n_in, int ntaps, int decim, float* y, int use_double)
 {
   size_t n_out = n_in / (size_t)decim;
   for (size_t n = 0; n < n_out; n++) {
     float ar = 0.0f, ai = 0.0f;
+    double dr = 0.0, di = 0.0;
     long newest = (long)(n * (size_t)decim);
     for (long k = newest - (ntaps - 1); k <= newest; k++) {
-      float xr = 0.0f, xi = 0.0f;
-      if (k >= 0) { xr = x[2 * k]; xi = x[2 * k + 1]; }
-      ar = ar + xr;
-      ai = ai + xi;
+      if (k < 0) continue;
+      ar = ar + x[2 * k]; ai = ai + x[2 * k + 1];
+      dr += x[2 * k]; di += x[2 * k + 1];
     }
-    y[2 * n] = ar;
-    y[2 * n + 1] = ai;
+    y[2 * n] = use_double ? (float)dr : ar;
+    y[2 * n + 1] = use_double ? (float)di : ai;
   }
   return n_out;
 }

@@ -42,6 +42,7 @@ class Oracle:
         L.gen2_oracle_decode_decimated.restype = C.c_int
         L.gen2_oracle_decode_segments.restype = C.c_int
         L.gen2_oracle_mf.restype = C.c_size_t
+        L.gen2_oracle_mf_variant.restype = C.c_size_t
         L.gen2_oracle_crc16.restype = C.c_uint16
         L.gen2_oracle_crc16_ok.restype = C.c_int
         L.gen2_oracle_cabsf.restype = C.c_float
@@ -51,11 +52,13 @@ class Oracle:
     def _p(a):
         return a.ctypes.data_as(C.c_void_p)
 
-    def mf(self, iq):
+    def mf(self, iq, variant=0):
+        """canonical matched filter (variant 0); 1 = sequential float32, 2 = float64 accumulation"""
         raw = np.ascontiguousarray(iq, dtype=np.complex64).view(np.float32)
         n = raw.size // 2
         y = np.zeros(2 * (n // self.cfg.decim + 1), dtype=np.float32)
-        ny = self.lib.gen2_oracle_mf(self._p(raw), C.c_size_t(n), self.cfg.ntaps, self.cfg.decim, self._p(y))
+        ny = self.lib.gen2_oracle_mf_variant(self._p(raw), C.c_size_t(n), self.cfg.ntaps, self.cfg.decim,
+                                             self._p(y), int(variant))
         return y[:2 * ny].view(np.complex64).copy()
 
     def gate(self, y, max_windows=4096, want_windows=False, want_avg=False):
