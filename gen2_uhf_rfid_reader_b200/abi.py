@@ -1,6 +1,6 @@
 """ctypes mirror of include/rfid_b200.h (structures and constants only).
 
-Kept separate from the library loader so that test infrastructure (oracle/) can
+Kept separate from the library loader so that test infrastructure can
 share the record layout without importing the CUDA library.
 """
 import ctypes as C

@@ -296,7 +296,7 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
   fused_fn fn = pick_kernel(ctx->cfg.decim);
   if (!fn) { ctx->last_error = "capture mode supports decim = 5 only in this build"; return RFID_B200_EINVAL; }
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t s = (cudaStream_t)stream;  // NULL = the (legacy) default stream, as documented
   FusedArgs A = ctx->layout;
   A.iq = reinterpret_cast<const float2*>(d_iq);
   A.n_raw = n_raw;

@@ -1,0 +1,95 @@
+"""CPU tests of host-side logic: synthetic generator, segment sharding, the world-size-2 gather (gloo)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from gen2_uhf_rfid_reader_b200 import abi, shard, synth
+
+
+def test_synth_is_deterministic_and_shard_invariant():
+    a = synth.make_capture(12, seed=9)
+    b = synth.make_capture(12, seed=9)
+    assert torch.equal(a["iq"], b["iq"])
+    part = synth.make_capture(4, seed=9, first_segment=8)
+    L = a["truth"]["segment_len"]
+    # per-segment protocol content (RN16, EPC, timing) depends only on (seed, segment id)
+    assert (part["truth"]["rn16"] == a["truth"]["rn16"][8:]).all()
+    assert (part["truth"]["epc"] == a["truth"]["epc"][8:]).all()
+    assert L == 16960 and a["iq"].numel() == 12 * L
+    assert (a["segments"]["offset"] == np.arange(12) * L).all()
+
+
+def test_synth_collisions_q4():
+    cap = synth.make_capture(64, seed=2, fixed_q=4, n_tags=8)
+    t = cap["truth"]
+    assert t["is_query"].sum() == 4 and t["is_query"][::16].all()
+    per_round = t["n_replies"].reshape(4, 16).sum(axis=1)
+    assert (per_round == 8).all()          # every tag answers in exactly one slot of its round
+    assert (t["n_replies"] >= 2).any()     # with 8 tags in 16 slots some slot collides
+
+
+def test_epc_frames_have_valid_crc():
+    fr = synth.make_epc_frames(np.arange(24, dtype=np.uint8).reshape(2, 12))
+    for f in fr:
+        assert synth.crc16_gen2(bytes(f[:14])) == (int(f[14]) << 8 | int(f[15]))
+
+
+@pytest.mark.parametrize("n,w", [(1000, 1), (1000, 8), (7, 4), (3, 8), (0, 2)])
+def test_shard_ranges_partition(n, w):
+    r = [shard.shard_range(n, k, w) for k in range(w)]
+    assert r[0][0] == 0 and r[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    assert max(e - b for b, e in r) <= shard.max_shard(n, w)
+
+
+def _gloo_worker(rank, world, port, n_seg, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle.pyoracle import Oracle  # the checker stands in for the GPU decode in this CPU test
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cap_all = synth.make_capture(n_seg, seed=31)
+    b, e = shard.shard_range(n_seg, rank, world)
+    L = cap_all["truth"]["segment_len"]
+    iq = cap_all["iq"].numpy()[b * L:e * L]
+    segs = abi.make_segments(np.arange(e - b) * L, [L] * (e - b))
+    recs, counts, _ = Oracle().decode_segments(iq, segs, max_per_seg=2)
+    shard.renumber_segments(recs, b)
+    res_t = torch.from_numpy(recs.reshape(-1).view(np.uint8).reshape(-1, 64).copy())
+    cnt_t = torch.from_numpy(counts.copy())
+    g_res, g_cnt = shard.gather_records(res_t, cnt_t, n_seg, 2)
+    if rank == 0:
+        out_q.put((g_res.numpy().tobytes(), g_cnt.numpy().tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_records_world2_gloo():
+    """N>1 path on CPU: two ranks decode disjoint shards, one all-gather, rank 0 sees the single-process result"""
+    import torch.multiprocessing as mp
+    n_seg = 5   # odd => unequal shards exercise the padding
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_seg, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res_b, cnt_b = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from oracle.pyoracle import Oracle
+    cap = synth.make_capture(n_seg, seed=31)
+    recs, counts, _ = Oracle().decode_segments(cap["iq"].numpy(), cap["segments"], max_per_seg=2)
+    got = np.frombuffer(res_b, dtype=abi.RESULT_DTYPE).reshape(n_seg, 2)
+    assert np.frombuffer(cnt_b, dtype=np.int32).tolist() == counts.tolist()
+    for f in recs.dtype.names:
+        assert got[f].tobytes() == recs[f].tobytes(), f
