@@ -115,22 +115,20 @@ void make_layout(const RxConfig& c, FusedArgs& L)
   L.off_ahist = off; off = align_up(off + L.ahist_size * 4, 16);
   L.off_tile_y = off; off += kTileStages * kTT * 8;
   L.off_tile_a = off; off += kTileStages * kTT * 4;
-  L.off_tile_d = off; off += kTileStages * kTT * 4;
+  L.off_tile_d = off; off += kTileStages * kTT * 4 + 64;  // + read-ahead pad of the running-sum loop
   L.ycl_size = next_pow2(kTT + c.dc_length);
   L.off_ycl = off; off = align_up(off + L.ycl_size * 8, 16);
-  L.off_e = off; off += 2 * kTT * 4;
+  L.off_e = off; off += 2 * (kTT + 16) * 4;
   L.off_win = off; off = align_up(off + c.len_epc * 8, 16);
-  L.off_M = off; off = align_up(off + c.len_epc * 4, 16);
   L.smem_bytes = off;
 }
 
 typedef void (*fused_fn)(const FusedArgs);
-fused_fn pick_kernel(int decim)
+fused_fn pick_kernel(const RxConfig& c)
 {
-  switch (decim) {
-    case 5: return rx_fused_kernel<5>;
-    default: return nullptr;
-  }
+  if (c.decim != 5) return nullptr;
+  if (c.mf_rem == 0 && c.mf_q == 5) return rx_fused_kernel<5, 5>;  // the reference configuration: 25 taps
+  return rx_fused_kernel<5, 0>;                                      // any other tap count
 }
 
 int grow(rfid_b200_ctx* ctx, void** p, size_t* have, size_t need)
@@ -222,7 +220,7 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
     e = cudaMemcpyAsync(ctx->d_gate, &init, offsetof(GateState, win_samples), cudaMemcpyHostToDevice, ctx->stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  fused_fn fn = pick_kernel(cfg.decim);
+  fused_fn fn = pick_kernel(cfg);
   if (e == cudaSuccess && fn)
     e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->layout.smem_bytes);
   if (e == cudaSuccess)
@@ -293,7 +291,7 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
   if ((reinterpret_cast<uintptr_t>(d_iq) & 15u) != 0) return RFID_B200_EINVAL;  // TMA bulk source alignment
   ctx->last_launches = 0;
   if (nseg == 0) return RFID_B200_OK;
-  fused_fn fn = pick_kernel(ctx->cfg.decim);
+  fused_fn fn = pick_kernel(ctx->cfg);
   if (!fn) { ctx->last_error = "capture mode supports decim = 5 only in this build"; return RFID_B200_EINVAL; }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;  // NULL = the (legacy) default stream, as documented

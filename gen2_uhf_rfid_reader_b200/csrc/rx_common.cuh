@@ -111,6 +111,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// wait for a phase that is not on this warp's critical path: let the hardware park the warp
+// (suspend-time hint, ns) instead of burning issue slots that the sequencer warps need
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000)
+{
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (!ok);
+}
 // 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar`
 // (SASS: UBLKCP).  dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)

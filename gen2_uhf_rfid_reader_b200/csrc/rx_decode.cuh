@@ -48,6 +48,7 @@ __device__ __forceinline__ int crc16_check(const uint32_t bits[4])
 
 // w: window samples (y - dc_est), n_avail samples; M: scratch for |w|^2 (EPC only, >= n_avail floats).
 // All 32 lanes of the warp must call; the result is valid in every lane.
+// M == nullptr: |w|^2 is evaluated at every gather of the period search instead of being staged.
 __device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, const float2* __restrict__ w,
                                                    int n_avail, float* __restrict__ M, WindowDecode& out)
 {
@@ -141,8 +142,10 @@ __device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, 
   }
 
   // ---- EPC: magn_squared_samples (gate_impl.cc:172,186)
-  for (int p = lane; p < n_avail; p += 32) M[p] = c_norm(w[p]);
-  __syncwarp();
+  if (M) {
+    for (int p = lane; p < n_avail; p += 32) M[p] = c_norm(w[p]);
+    __syncwarp();
+  }
   // ---- symbol-period search (:151-165): 20 candidates, 256 sequential gathers each
   const int number_steps = 20;
   const float min_val = c.t_min, max_val = c.t_max;
@@ -154,7 +157,7 @@ __device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, 
 #pragma unroll 4
     for (int i = 0; i < 256; i++) {
       int p = (int)f_add(f_mul((float)i, Tt), (float)index);  // :161
-      e = f_add(e, M[p]);
+      e = f_add(e, M ? M[p] : c_norm(w[p]));
     }
     energy = e;
     e_idx = lane;

@@ -8,17 +8,20 @@
 // gate_impl::general_work (lib/gate_impl.cc:85-200) and
 // tag_decoder_impl::general_work (lib/tag_decoder_impl.cc:196-397).
 //
-// CTA = 4 warps with fixed roles, connected by mbarrier pipelines:
-//   warp 0      sequencer: everything that is order-dependent in the reference -- the two float
-//               running means (avg_ampl: one dependent FADD per sample on lane 0; dc_est: lanes 1,2),
-//               the edge/pulse state machine (bit-mask hopping, a few steps per command), window
-//               bookkeeping.  Lane-parallel inside a tile for everything else (thresholds, DC ring
-//               differences, window emission).
-//   warps 1..2  workers: wait for the TMA bulk copy of the next raw tile, block-sum matched filter,
-//               |y| (exact cabsf), amplitude-ring difference /win_length  -> tile stage.
-//   warp 3      decoder: when the sequencer closes a window, decodes it from shared memory
-//               (preamble correlation, channel estimate, FM0 decisions, period search, CRC-16)
-//               and writes the result record.
+// CTA = 4 warps with fixed roles (rotated over the hardware warps by blockIdx so that the
+// latency-critical warps of co-resident CTAs spread over the four SM sub-partitions):
+//   sequencer   everything that is order-dependent in the reference.  Per 128-sample tile it runs ONE
+//               pass of three simultaneous float running sums -- lane 0: avg_ampl over tile k
+//               (gate_impl.cc:131), lanes 1,2: dc_est.re/.im over the closed samples of tile k-1
+//               (gate_impl.cc:141) -- then finishes tile k-1 (window emission with the now-known DC
+//               estimate, window hand-off to the decoder) and runs thresholds + the edge/pulse state
+//               machine of tile k as bit-mask hopping (a few steps per reader command).
+//   workers x2  wait for the TMA bulk copy of the next raw tile, block-sum matched filter, |y|
+//               (exact cabsf), amplitude-ring difference / win_length  -> tile stage.
+//   decoder     decodes each closed window from shared memory (preamble correlation, channel
+//               estimate, FM0 decisions, period search, CRC-16) and writes the result record.
+// Hand-offs use named barriers (bar.arrive / bar.sync): a waiting warp is parked by the hardware
+// and costs no issue slots; only the TMA completion uses an mbarrier (transaction count).
 #pragma once
 
 #include "rx_common.cuh"
@@ -26,12 +29,32 @@
 
 namespace rfid_b200 {
 
+#ifdef RFID_B200_PHASE_PROFILE
+// developer aid: per-phase clock64() sums of the sequencer / worker warp of CTA 0..N, written to the window tap
+#define PH_DECL long long ph_t0 = clock64(), ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PH_MARK(i) { long long ph_t1 = clock64(); ph_acc[i] += ph_t1 - ph_t0; ph_t0 = ph_t1; }
+#define PH_DUMP(base) if (lane == 0 && A.window_tap) { long long* o = reinterpret_cast<long long*>(A.window_tap) + (size_t)blockIdx.x * 16 + (base); for (int i = 0; i < 8; i++) o[i] = ph_acc[i]; }
+#else
+#define PH_DECL
+#define PH_MARK(i)
+#define PH_DUMP(base)
+#endif
+
 constexpr int kTT = 128;          // decimated samples per tile
 constexpr int kRawStages = 3;
-constexpr int kTileStages = 3;
+constexpr int kTileStages = 3;    // >= 3: tile k-1 is still being finished while tile k+1 is produced
 constexpr int kWorkerWarps = 2;
 constexpr int kWorkerThreads = kWorkerWarps * 32;
 constexpr int kFusedThreads = 32 * (2 + kWorkerWarps);
+constexpr int kMaxTileEvents = 6;
+
+enum : int {
+  BAR_WORKERS = 1,      // the two worker warps (64)
+  BAR_TILE_FULL = 2,    // +stage: workers arrive (64), sequencer syncs (32)
+  BAR_TILE_EMPTY = 5,   // +stage: sequencer arrives (32), workers sync (64)
+  BAR_WIN_READY = 8,    // sequencer arrives, decoder syncs
+  BAR_WIN_FREE = 9      // decoder arrives, sequencer syncs
+};
 
 struct FusedArgs {
   const float2* iq;              // raw capture (device), 16-byte aligned
@@ -49,18 +72,29 @@ struct FusedArgs {
   int off_ahist, ahist_size;     // float[ahist_size]
   int off_tile_y, off_tile_a, off_tile_d;
   int off_ycl, ycl_size;         // float2[ycl_size]
-  int off_e;                     // float[2][kTT]
-  int off_win, off_M;
+  int off_e;                     // float[2][kTT + 16]
+  int off_win;
   int smem_bytes;
 };
 
-struct FusedBars {
-  uint64_t raw_full[kRawStages];
-  uint64_t tile_full[kTileStages];
-  uint64_t tile_empty[kTileStages];
-  uint64_t win_ready, win_free;
-  int meta_kind, meta_open, meta_ordinal, meta_len;
+struct TileEvent {
+  int type;  // 1 = gate opens at tile position pos (trigger sample), 2 = window ends before position pos
+  int pos;
+  int a, b, c, d;  // open: a = index of the trigger in the tile's closed-sample list, b = open index, c = store
+                   // close: a = kind, b = ordinal, c = length, d = open index
 };
+
+struct FusedShared {
+  uint64_t raw_full[kRawStages];
+  int meta_kind, meta_open, meta_ordinal, meta_len;
+  int n_ev;
+  TileEvent ev[kMaxTileEvents];
+};
+
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+{
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ int next_set128(unsigned long long lo, unsigned long long hi, int pos)
 {
@@ -76,17 +110,37 @@ __device__ __forceinline__ int next_set128(unsigned long long lo, unsigned long 
   return 128;
 }
 
-// sequential in-place running sum: acc = acc + buf[i]; buf[i] = acc   (one rounding per step)
+__device__ __forceinline__ void chain8(float4& u, float4& v, float& acc)
+{
+  acc = f_add(acc, u.x); u.x = acc;
+  acc = f_add(acc, u.y); u.y = acc;
+  acc = f_add(acc, u.z); u.z = acc;
+  acc = f_add(acc, u.w); u.w = acc;
+  acc = f_add(acc, v.x); v.x = acc;
+  acc = f_add(acc, v.y); v.y = acc;
+  acc = f_add(acc, v.z); v.z = acc;
+  acc = f_add(acc, v.w); v.w = acc;
+}
+
+// Sequential in-place running sum: acc = acc + buf[i]; buf[i] = acc (one rounding per step, the order of
+// the reference's recurrences).  The next 8 inputs are always in flight while 8 dependent adds retire, so
+// the loop runs at the FADD dependency latency.  May READ up to 16 floats past buf[n-1] (callers pad).
 __device__ __forceinline__ void chain_inplace(float* buf, int n, float& acc)
 {
   int i = 0;
-  for (; i + 4 <= n; i += 4) {
-    float4 v = *reinterpret_cast<float4*>(buf + i);
-    acc = f_add(acc, v.x); v.x = acc;
-    acc = f_add(acc, v.y); v.y = acc;
-    acc = f_add(acc, v.z); v.z = acc;
-    acc = f_add(acc, v.w); v.w = acc;
-    *reinterpret_cast<float4*>(buf + i) = v;
+  if (n >= 16) {
+    float4 a0 = *reinterpret_cast<const float4*>(buf), a1 = *reinterpret_cast<const float4*>(buf + 4);
+    for (; i + 16 <= n; i += 16) {
+      float4 b0 = *reinterpret_cast<const float4*>(buf + i + 8), b1 = *reinterpret_cast<const float4*>(buf + i + 12);
+      chain8(a0, a1, acc);
+      *reinterpret_cast<float4*>(buf + i) = a0;
+      *reinterpret_cast<float4*>(buf + i + 4) = a1;
+      a0 = *reinterpret_cast<const float4*>(buf + i + 16);
+      a1 = *reinterpret_cast<const float4*>(buf + i + 20);
+      chain8(b0, b1, acc);
+      *reinterpret_cast<float4*>(buf + i + 8) = b0;
+      *reinterpret_cast<float4*>(buf + i + 12) = b1;
+    }
   }
   for (; i < n; i++) {
     acc = f_add(acc, buf[i]);
@@ -130,14 +184,16 @@ __device__ __forceinline__ void issue_tile_load(const FusedArgs& A, const rfid_b
   if (bytes) tma_load_1d(stage, A.iq + abs_start, bytes, bar);
 }
 
-template <int DECIM>
+// MFQ > 0: ntaps == MFQ * DECIM (compile-time unrolled block sums); MFQ == 0: generic ntaps
+template <int DECIM, int MFQ>
 __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs A)
 {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ FusedBars B;
+  __shared__ FusedShared B;
 
   const int seg = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int warp = ((threadIdx.x >> 5) + blockIdx.x) & 3;  // role: 0 sequencer, 1..2 workers, 3 decoder
   const RxConfig& C = A.cfg;
   const rfid_b200_segment sg = A.segs[seg];
   const int n_out = (int)(sg.length / DECIM);
@@ -152,60 +208,59 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
   float* tile_d = reinterpret_cast<float*>(smem + A.off_tile_d);
   float2* ycl = reinterpret_cast<float2*>(smem + A.off_ycl);
   float* e_re = reinterpret_cast<float*>(smem + A.off_e);
-  float* e_im = e_re + kTT;
+  float* e_im = e_re + kTT + 16;
   float2* win = reinterpret_cast<float2*>(smem + A.off_win);
-  float* Msq = reinterpret_cast<float*>(smem + A.off_M);
 
   // ---- init: zero the history rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56;
-  //      x[<0] = +0 for the matched filter), set up the barriers
+  //      x[<0] = +0 for the matched filter), set up the TMA barriers
   for (int i = threadIdx.x; i < A.bhist_size * (C.mf_rem ? 2 : 1); i += kFusedThreads) bhist[i] = make_float2(0.f, 0.f);
   for (int i = threadIdx.x; i < A.ahist_size; i += kFusedThreads) ahist[i] = 0.f;
   for (int i = threadIdx.x; i < A.ycl_size; i += kFusedThreads) ycl[i] = make_float2(0.f, 0.f);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; s++) mbar_init(&B.raw_full[s], 1);
-    for (int s = 0; s < kTileStages; s++) {
-      mbar_init(&B.tile_full[s], kWorkerWarps);
-      mbar_init(&B.tile_empty[s], 1);
-    }
-    mbar_init(&B.win_ready, 1);
-    mbar_init(&B.win_free, 1);
+    B.n_ev = 0;
     mbar_fence_init();
   }
   __syncthreads();
 
   if (warp >= 1 && warp <= kWorkerWarps) {
     // =========================================================== workers
-    const int wt = threadIdx.x - 32;
+    const int wt = (warp - 1) * 32 + lane;
     if (wt == 0) {
       for (int k = 0; k < kRawStages && k < ntiles; k++)
         issue_tile_load<DECIM>(A, sg, k, raw + (size_t)k * A.raw_stage_samples, &B.raw_full[k]);
     }
     const int bmask = A.bhist_size - 1, amask = A.ahist_size - 1;
     const float winlen_f = (float)C.win_length;
+    PH_DECL
     for (int k = 0; k < ntiles; k++) {
       const int rs = k % kRawStages, ts = k % kTileStages;
       const float2* stage = raw + (size_t)rs * A.raw_stage_samples;
-      const long long start = tile_load_start<DECIM>(sg.offset, k);
+      // stage index of raw sample x[D*n - (D-1) + j] for tile-local output t:  D*t - (D-1) + j - delta
+      const int delta = (int)(tile_load_start<DECIM>(sg.offset, k) - (long long)DECIM * k * kTT);
+      const int nvalid = min(kTT, n_out - k * kTT);
+      PH_MARK(0)
       mbar_wait(&B.raw_full[rs], (k / kRawStages) & 1);
+      PH_MARK(1)
       // ---- block sums B(n) = x[D*n-D+1 .. D*n], ascending (and the partial block when ntaps % D != 0)
 #pragma unroll
       for (int r = 0; r < kTT / kWorkerThreads; r++) {
         const int t = wt + r * kWorkerThreads;
-        const int n = k * kTT + t;
-        if (n < n_out) {
-          const long long base = (long long)DECIM * n - (DECIM - 1) - start;  // stage index of x[D*n-D+1]
+        if (t < nvalid) {
+          const int n = k * kTT + t;
+          const int base = DECIM * t - (DECIM - 1) - delta;
           float2 x[DECIM];
 #pragma unroll
           for (int j = 0; j < DECIM; j++) {
-            long long si = base + j;
             // only the very first block of a segment reaches before sample 0 (reads as +0)
-            x[j] = ((long long)DECIM * n - (DECIM - 1) + j >= 0) ? stage[si] : make_float2(0.f, 0.f);
+            const bool before = (k == 0) && (DECIM * t - (DECIM - 1) + j < 0);
+            x[j] = before ? make_float2(0.f, 0.f) : stage[base + j];
           }
           float2 b = x[0];
 #pragma unroll
           for (int j = 1; j < DECIM; j++) b = c_add(b, x[j]);
           bhist[n & bmask] = b;
-          if (C.mf_rem) {  // P(n): newest mf_rem samples of the block, ascending (static indexing only)
+          if (MFQ == 0 && C.mf_rem) {  // P(n): newest mf_rem samples of the block, ascending (static indexing only)
             float2 p = make_float2(0.f, 0.f);
             bool started = false;
 #pragma unroll
@@ -219,27 +274,36 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
           }
         }
       }
-      named_bar_sync(1, kWorkerThreads);  // raw stage rs fully consumed, block sums visible
+      PH_MARK(2)
+      named_bar_sync(BAR_WORKERS, kWorkerThreads);  // raw stage rs fully consumed, block sums visible
       if (wt == 0 && k + kRawStages < ntiles)
         issue_tile_load<DECIM>(A, sg, k + kRawStages, raw + (size_t)rs * A.raw_stage_samples, &B.raw_full[rs]);
-      mbar_wait(&B.tile_empty[ts], ((k / kTileStages) & 1) ^ 1);
+      PH_MARK(3)
+      if (k >= kTileStages) named_bar_sync(BAR_TILE_EMPTY + ts, 96);  // the sequencer is done with tile k - 3
+      PH_MARK(4)
       // ---- y[n] = ((P(n-q) + B(n-q+1)) + ...) + B(n);  a = |y|
       float a_reg[kTT / kWorkerThreads];
 #pragma unroll
       for (int r = 0; r < kTT / kWorkerThreads; r++) {
         const int t = wt + r * kWorkerThreads;
-        const int n = k * kTT + t;
         a_reg[r] = 0.f;
-        if (n < n_out) {
+        if (t < nvalid) {
+          const int n = k * kTT + t;
           float2 y;
-          int m = n - C.mf_q + 1;
-          if (C.mf_rem) {
-            y = phist[(n - C.mf_q) & bmask];
+          if (MFQ > 0) {
+            y = bhist[(n - MFQ + 1) & bmask];
+#pragma unroll
+            for (int m = MFQ - 2; m >= 0; m--) y = c_add(y, bhist[(n - m) & bmask]);
           } else {
-            y = bhist[m & bmask];
-            m++;
+            int m = n - C.mf_q + 1;
+            if (C.mf_rem) {
+              y = phist[(n - C.mf_q) & bmask];
+            } else {
+              y = bhist[m & bmask];
+              m++;
+            }
+            for (; m <= n; m++) y = c_add(y, bhist[m & bmask]);
           }
-          for (; m <= n; m++) y = c_add(y, bhist[m & bmask]);
           const float a = cabsf_ref(y.x, y.y);  // gate_impl.cc:130
           tile_y[ts * kTT + t] = y;
           tile_a[ts * kTT + t] = a;
@@ -247,58 +311,128 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
           a_reg[r] = a;
         }
       }
-      named_bar_sync(1, kWorkerThreads);  // amplitude ring visible
+      PH_MARK(5)
+      named_bar_sync(BAR_WORKERS, kWorkerThreads);  // amplitude ring visible
+      PH_MARK(6)
       // ---- (a - win_samples[win_index]) / win_length   (gate_impl.cc:131)
 #pragma unroll
       for (int r = 0; r < kTT / kWorkerThreads; r++) {
         const int t = wt + r * kWorkerThreads;
-        const int n = k * kTT + t;
-        if (n < n_out) tile_d[ts * kTT + t] = f_div(f_sub(a_reg[r], ahist[(n - C.win_length) & amask]), winlen_f);
+        if (t < nvalid) {
+          const int n = k * kTT + t;
+          tile_d[ts * kTT + t] = f_div(f_sub(a_reg[r], ahist[(n - C.win_length) & amask]), winlen_f);
+        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&B.tile_full[ts]);
+      __threadfence_block();
+      named_bar_arrive(BAR_TILE_FULL + ts, 96);
+      PH_MARK(7)
     }
+    if (wt == 0) { PH_DUMP(8) }
   } else if (warp == 0) {
     // =========================================================== sequencer
     float acc = 0.f;  // lane 0: avg_ampl, lane 1: dc_est.re, lane 2: dc_est.im
+    // --- gate state machine (runs one tile ahead of the window emission)
     bool sig_pos = false;          // signal_state, starts NEG_EDGE (gate_impl.cc:45)
     int n_samples = 0, num_pulses = 0;
     bool gate_open = false;
     int to_ungate = C.len_rn16;    // first SEEK is for an RN16 (global_vars.cc:47, reader_impl.cc:262)
-    int wcount = 0, wsignalled = 0;
+    int wcount = 0;
     int n_closed = 0;              // closed-sample ordinal (index into the DC ring stream)
-    int wpos = 0, open_idx = 0;
+    int open_idx = 0;
+    bool cur_store = false;
     int nq = 1;                    // n_queries_sent after START -> SEND_QUERY (reader_impl.cc:259)
-    bool terminated = false, store_this = false;
+    bool terminated = false;
+    int n_e = 0;                   // closed samples of the tile whose DC chain is still to run
+    // --- emission state (tile k-1)
+    bool f_open = false, f_store = false;
+    int f_wpos = 0, pending_free = 0;
     float2 dc_open = make_float2(0.f, 0.f);
     const int ymask = A.ycl_size - 1;
     const float dclen_f = (float)C.dc_length;
     const int half_pw = C.n_PW / 2;
+    PH_DECL
 
-    for (int k = 0; k < ntiles; k++) {
+    for (int k = 0; k <= ntiles; k++) {
       const int ts = k % kTileStages;
-      mbar_wait(&B.tile_full[ts], (k / kTileStages) & 1);
-      const int nvalid = min(kTT, n_out - k * kTT);
+      const int nvalid = k < ntiles ? min(kTT, n_out - k * kTT) : 0;
       float* davg = tile_d + ts * kTT;
-      const float* ta = tile_a + ts * kTT;
-      const float2* ty = tile_y + ts * kTT;
-      if (!terminated) {
-        // ---- avg_ampl recurrence (gate_impl.cc:131): one dependent add per sample, lane 0
-        if (lane == 0) chain_inplace(davg, nvalid, acc);
+      PH_MARK(0)
+      if (k < ntiles) named_bar_sync(BAR_TILE_FULL + ts, 96);
+      PH_MARK(1)
+      // ---- 1. the three recurrences, one pass: avg_ampl over tile k, dc_est over tile k-1's closed samples
+      if (lane < 3) chain_inplace(lane == 0 ? davg : (lane == 1 ? e_re : e_im), lane == 0 ? nvalid : n_e, acc);
+      __syncwarp();
+      PH_MARK(2)
+      // ---- 2. finish tile k-1: window emission (gate_impl.cc:173,187) and hand-off to the decoder
+      if (k >= 1) {
+        const int pts = (k - 1) % kTileStages;
+        const float2* py = tile_y + pts * kTT;
+        const int pvalid = min(kTT, n_out - (k - 1) * kTT);
+        const int nev = B.n_ev;
+        int pos = 0;
+        for (int e = 0; e <= nev; e++) {
+          const bool last = e == nev;
+          const int etype = last ? 0 : B.ev[e].type;
+          const int epos = last ? pvalid : B.ev[e].pos;
+          if (f_open) {
+            const int take = epos - pos;  // an open event cannot occur while the gate is open
+            if (f_store)
+              for (int j = lane; j < take; j += 32) win[f_wpos + j] = c_sub(py[pos + j], dc_open);
+            f_wpos += take;
+            pos = epos;
+          }
+          if (etype == 2) {
+            // window complete: hand it to the decoder
+            f_open = false;
+            if (f_store) {
+              __syncwarp();
+              if (lane == 0) { B.meta_kind = B.ev[e].a; B.meta_ordinal = B.ev[e].b; B.meta_len = B.ev[e].c; B.meta_open = B.ev[e].d; }
+              __threadfence_block();
+              __syncwarp();
+              named_bar_arrive(BAR_WIN_READY, 64);
+              pending_free++;
+            }
+            pos = epos;
+          } else if (etype == 1) {
+            // READER COMMAND DETECTED (gate_impl.cc:164-180): dc_est right after the trigger sample
+            const int j = B.ev[e].a;
+            dc_open = make_float2(e_re[j], e_im[j]);
+            f_store = B.ev[e].c != 0;
+            f_open = true;
+            if (f_store) {
+              while (pending_free > 0) { named_bar_sync(BAR_WIN_FREE, 64); pending_free--; }  // window buffer free
+              if (lane == 0) win[0] = c_sub(py[epos], dc_open);
+            }
+            f_wpos = 1;
+            pos = epos + 1;
+          }
+        }
         __syncwarp();
-        // ---- threshold flags (gate_impl.cc:136,148,154)
+        if (k - 1 + kTileStages < ntiles) {
+          __threadfence_block();
+          named_bar_arrive(BAR_TILE_EMPTY + pts, 96);  // stage of tile k-1 may be refilled
+        }
+      }
+      PH_MARK(3)
+      // ---- 3. thresholds + state machine of tile k; collect its closed samples for the DC chain
+      n_e = 0;
+      int nev = 0;
+      if (k < ntiles && !terminated) {
+        const float* ta = tile_a + ts * kTT;
+        const float2* ty = tile_y + ts * kTT;
         unsigned lt[4], gt[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const int i = r * 32 + lane;
-          bool v = i < nvalid;
-          float thr = v ? f_mul(davg[i], kThreshFraction) : 0.f;
-          float a = v ? ta[i] : 0.f;
+          const bool v = i < nvalid;
+          const float thr = v ? f_mul(davg[i], kThreshFraction) : 0.f;  // gate_impl.cc:136
+          const float a = v ? ta[i] : 0.f;
           lt[r] = __ballot_sync(0xffffffffu, v && a < thr);
           gt[r] = __ballot_sync(0xffffffffu, v && a > thr);
         }
         const unsigned long long LT_lo = lt[0] | ((unsigned long long)lt[1] << 32), LT_hi = lt[2] | ((unsigned long long)lt[3] << 32);
         const unsigned long long GT_lo = gt[0] | ((unsigned long long)gt[1] << 32), GT_hi = gt[2] | ((unsigned long long)gt[3] << 32);
+        PH_MARK(4)
 
         int pos = 0;
         while (pos < nvalid) {
@@ -322,50 +456,43 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
                 n_samples = 0; sig_pos = true; pos = p_rise + 1;
               }
             }
-            // ---- DC tracker over the closed run [run_start, pos) (gate_impl.cc:141-143); the run
-            //      includes the trigger sample, as in the reference (update precedes the open test)
+            // ---- DC tracker inputs for the closed run [run_start, pos) (gate_impl.cc:141-143); the run
+            //      includes the trigger sample, as in the reference (the update precedes the open test)
             const int len = pos - run_start;
             for (int j = lane; j < len; j += 32) ycl[(n_closed + j) & ymask] = ty[run_start + j];
             __syncwarp();
             for (int j = lane; j < len; j += 32) {
               const float2 yv = ty[run_start + j];
               const float2 old = ycl[(n_closed + j - C.dc_length) & ymask];
-              e_re[j] = f_div(f_sub(yv.x, old.x), dclen_f);
-              e_im[j] = f_div(f_sub(yv.y, old.y), dclen_f);
+              e_re[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
+              e_im[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
             }
-            __syncwarp();
-            if (lane == 1) chain_inplace(e_re, len, acc);
-            if (lane == 2) chain_inplace(e_im, len, acc);
-            __syncwarp();
             n_closed += len;
+            n_e += len;
             if (opened) {
-              // READER COMMAND DETECTED (gate_impl.cc:164-180)
-              dc_open = make_float2(__shfl_sync(0xffffffffu, acc, 1), __shfl_sync(0xffffffffu, acc, 2));
               gate_open = true;
               open_idx = k * kTT + pos - 1;
-              store_this = wcount < A.max_windows;
-              if (store_this && wsignalled > 0) mbar_wait(&B.win_free, (wsignalled - 1) & 1);  // window buffer free
-              if (store_this && lane == 0) win[0] = c_sub(ty[pos - 1], dc_open);
-              wpos = 1;
+              cur_store = wcount < A.max_windows;
+              if (lane == 0 && nev < kMaxTileEvents) {
+                TileEvent& ev = B.ev[nev];
+                ev.type = 1; ev.pos = pos - 1; ev.a = n_e - 1; ev.b = open_idx; ev.c = cur_store ? 1 : 0; ev.d = 0;
+              }
+              nev++;
               num_pulses = 0;
               n_samples = 1;
             }
           } else {
-            // ---- open: pass samples through with the frozen DC estimate (gate_impl.cc:182-195)
+            // ---- open: the samples pass through (gate_impl.cc:182-195); emitted one tile later
             const int take = min(to_ungate - n_samples, nvalid - pos);
-            if (store_this)
-              for (int j = lane; j < take; j += 32) win[wpos + j] = c_sub(ty[pos + j], dc_open);
-            wpos += take; n_samples += take; pos += take;
+            n_samples += take; pos += take;
             if (n_samples >= to_ungate) {
               gate_open = false;
               const int kind = wcount & 1;  // windows alternate RN16, EPC
-              if (store_this) {
-                __syncwarp();
-                if (lane == 0) { B.meta_kind = kind; B.meta_open = open_idx; B.meta_ordinal = wcount; B.meta_len = to_ungate; }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&B.win_ready);
-                wsignalled++;
+              if (lane == 0 && nev < kMaxTileEvents) {
+                TileEvent& ev = B.ev[nev];
+                ev.type = 2; ev.pos = pos; ev.a = kind; ev.b = wcount; ev.c = to_ungate; ev.d = open_idx;
               }
+              nev++;
               wcount++;
               // the Gen2 logic answers (ACK after RN16 -> GATE_SEEK_EPC, Query/QueryRep after EPC ->
               // GATE_SEEK_RN16) and the next gate call applies it (gate_impl.cc:112-123)
@@ -379,26 +506,29 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
           }
         }
       }
+      if (lane == 0) B.n_ev = min(nev, kMaxTileEvents);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&B.tile_empty[ts]);
+      PH_MARK(5)
     }
+    PH_DUMP(0)
     // ---- shut the decoder down, publish the window count
-    if (wsignalled > 0) mbar_wait(&B.win_free, (wsignalled - 1) & 1);
+    while (pending_free > 0) { named_bar_sync(BAR_WIN_FREE, 64); pending_free--; }
     if (lane == 0) {
       B.meta_kind = -1;
       A.counts[seg] = wcount;
     }
+    __threadfence_block();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&B.win_ready);
+    named_bar_arrive(BAR_WIN_READY, 64);
   } else {
     // =========================================================== decoder
-    for (int j = 0;; j++) {
-      mbar_wait(&B.win_ready, j & 1);
+    for (;;) {
+      named_bar_sync(BAR_WIN_READY, 64);
       const int kind = B.meta_kind;
       if (kind < 0) break;
       const int ordinal = B.meta_ordinal, open_idx = B.meta_open, len = B.meta_len;
       WindowDecode wd;
-      decode_window_warp(C, kind, win, len, Msq, wd);
+      decode_window_warp(C, kind, win, len, nullptr, wd);
       rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
       if (lane == 0) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
       if (A.window_tap) {
@@ -406,7 +536,7 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
         for (int p = lane; p < len; p += 32) tap[p] = win[p];
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&B.win_free);
+      named_bar_arrive(BAR_WIN_FREE, 64);
     }
   }
 }
