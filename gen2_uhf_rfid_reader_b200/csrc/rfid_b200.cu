@@ -104,21 +104,31 @@ int derive_config(const rfid_b200_params& p, RxConfig& c)
 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+bool fast_path_ok(const RxConfig& c) { return c.win_length <= kTT && c.dc_length <= kTT; }
+
 void make_layout(const RxConfig& c, FusedArgs& L)
 {
+  const bool spec = fast_path_ok(c);
   int off = 0;
   L.raw_stage_samples = c.decim * kTT + 2;
   L.off_raw = off; off = align_up(off + kRawStages * L.raw_stage_samples * 8, 16);
   L.bhist_size = next_pow2(kTT + c.mf_q + 2);
   L.off_bhist = off; off = align_up(off + L.bhist_size * 8 * (c.mf_rem ? 2 : 1), 16);
-  L.ahist_size = next_pow2(kTT + c.win_length);
-  L.off_ahist = off; off = align_up(off + L.ahist_size * 4, 16);
   L.off_tile_y = off; off += kTileStages * kTT * 8;
   L.off_tile_a = off; off += kTileStages * kTT * 4;
   L.off_tile_d = off; off += kTileStages * kTT * 4 + 64;  // + read-ahead pad of the running-sum loop
-  L.ycl_size = next_pow2(kTT + c.dc_length);
-  L.off_ycl = off; off = align_up(off + L.ycl_size * 8, 16);
-  L.off_e = off; off += 2 * (kTT + 16) * 4;
+  L.ahist_size = L.ycl_size = 0;
+  L.off_ahist = L.off_ycl = L.off_e = L.off_etile = L.off_snap = 0;
+  if (spec) {
+    L.off_etile = off; off += kTileStages * 2 * kTT * 4 + 64;
+    L.off_snap = off; off = align_up(off + c.dc_length * 8, 16);
+  } else {
+    L.ahist_size = next_pow2(kTT + c.win_length);
+    L.off_ahist = off; off = align_up(off + L.ahist_size * 4, 16);
+    L.ycl_size = next_pow2(kTT + c.dc_length);
+    L.off_ycl = off; off = align_up(off + L.ycl_size * 8, 16);
+    L.off_e = off; off += 2 * (kTT + 16) * 4;
+  }
   L.off_win = off; off = align_up(off + c.len_epc * 8, 16);
   L.smem_bytes = off;
 }
@@ -127,8 +137,11 @@ typedef void (*fused_fn)(const FusedArgs);
 fused_fn pick_kernel(const RxConfig& c)
 {
   if (c.decim != 5) return nullptr;
-  if (c.mf_rem == 0 && c.mf_q == 5) return rx_fused_kernel<5, 5>;  // the reference configuration: 25 taps
-  return rx_fused_kernel<5, 0>;                                      // any other tap count
+  if (fast_path_ok(c)) {
+    if (c.mf_rem == 0 && c.mf_q == 5) return rx_fused_kernel<5, 5, true>;  // the reference configuration: 25 taps
+    return rx_fused_kernel<5, 0, true>;
+  }
+  return rx_fused_kernel<5, 0, false>;  // long rings (raw rates above 5 MS/s) and any tap count
 }
 
 int grow(rfid_b200_ctx* ctx, void** p, size_t* have, size_t need)
@@ -223,6 +236,8 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
   fused_fn fn = pick_kernel(cfg);
   if (e == cudaSuccess && fn)
     e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->layout.smem_bytes);
+  if (e == cudaSuccess && fn)
+    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute((const void*)decode_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              cfg.len_epc * 12 + 64);

@@ -41,20 +41,38 @@ namespace rfid_b200 {
 #endif
 
 constexpr int kTT = 128;          // decimated samples per tile
-constexpr int kRawStages = 3;
+constexpr int kRawStages = 2;
 constexpr int kTileStages = 3;    // >= 3: tile k-1 is still being finished while tile k+1 is produced
 constexpr int kWorkerWarps = 2;
 constexpr int kWorkerThreads = kWorkerWarps * 32;
 constexpr int kFusedThreads = 32 * (2 + kWorkerWarps);
 constexpr int kMaxTileEvents = 6;
 
+// named barrier ids (immediates, so that ptxas reserves 8 and not all 16 hardware barriers per CTA)
 enum : int {
   BAR_WORKERS = 1,      // the two worker warps (64)
   BAR_TILE_FULL = 2,    // +stage: workers arrive (64), sequencer syncs (32)
-  BAR_TILE_EMPTY = 5,   // +stage: sequencer arrives (32), workers sync (64)
-  BAR_WIN_READY = 8,    // sequencer arrives, decoder syncs
-  BAR_WIN_FREE = 9      // decoder arrives, sequencer syncs
+  BAR_TILE_EMPTY = 5    // +stage: sequencer arrives (32), workers sync (64)
 };
+
+template <int BASE>
+__device__ __forceinline__ void bar_sync_stage(int s, int n)
+{
+  if (s == 0) asm volatile("bar.sync %0, %1;" ::"n"((int)BASE), "r"(n) : "memory");
+  else if (s == 1) asm volatile("bar.sync %0, %1;" ::"n"((int)(BASE + 1)), "r"(n) : "memory");
+  else asm volatile("bar.sync %0, %1;" ::"n"((int)(BASE + 2)), "r"(n) : "memory");
+}
+template <int BASE>
+__device__ __forceinline__ void bar_arrive_stage(int s, int n)
+{
+  if (s == 0) asm volatile("bar.arrive %0, %1;" ::"n"((int)BASE), "r"(n) : "memory");
+  else if (s == 1) asm volatile("bar.arrive %0, %1;" ::"n"((int)(BASE + 1)), "r"(n) : "memory");
+  else asm volatile("bar.arrive %0, %1;" ::"n"((int)(BASE + 2)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_sync_workers()
+{
+  asm volatile("bar.sync 1, 64;" ::: "memory");
+}
 
 struct FusedArgs {
   const float2* iq;              // raw capture (device), 16-byte aligned
@@ -71,8 +89,10 @@ struct FusedArgs {
   int off_bhist, bhist_size;     // float2[bhist_size] (+ partial-block ring right after it when mf_rem > 0)
   int off_ahist, ahist_size;     // float[ahist_size]
   int off_tile_y, off_tile_a, off_tile_d;
-  int off_ycl, ycl_size;         // float2[ycl_size]
-  int off_e;                     // float[2][kTT + 16]
+  int off_ycl, ycl_size;         // float2[ycl_size]                       (generic path)
+  int off_e;                     // float[2][kTT + 16]                      (generic path)
+  int off_etile;                 // float[kTileStages][2][kTT] (+pad)       (fast path: workers' DC-ring differences)
+  int off_snap;                  // float2[dc_length]: dc ring snapshot taken when the gate opens (fast path)
   int off_win;
   int smem_bytes;
 };
@@ -86,15 +106,11 @@ struct TileEvent {
 
 struct FusedShared {
   uint64_t raw_full[kRawStages];
+  uint64_t win_ready, win_free;
   int meta_kind, meta_open, meta_ordinal, meta_len;
   int n_ev;
   TileEvent ev[kMaxTileEvents];
 };
-
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
-{
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 __device__ __forceinline__ int next_set128(unsigned long long lo, unsigned long long hi, int pos)
 {
@@ -184,8 +200,11 @@ __device__ __forceinline__ void issue_tile_load(const FusedArgs& A, const rfid_b
   if (bytes) tma_load_1d(stage, A.iq + abs_start, bytes, bar);
 }
 
-// MFQ > 0: ntaps == MFQ * DECIM (compile-time unrolled block sums); MFQ == 0: generic ntaps
-template <int DECIM, int MFQ>
+// MFQ > 0: ntaps == MFQ * DECIM (compile-time unrolled block sums); MFQ == 0: generic ntaps.
+// SPEC: win_length <= kTT and dc_length <= kTT (true up to 5 MS/s raw): the amplitude / DC ring lookbacks
+// come straight from the time-indexed tile stages and the workers pre-compute the DC-ring differences, so
+// on a tile without gate activity the sequencer only runs its running sums.
+template <int DECIM, int MFQ, bool SPEC>
 __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs A)
 {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -209,15 +228,23 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
   float2* ycl = reinterpret_cast<float2*>(smem + A.off_ycl);
   float* e_re = reinterpret_cast<float*>(smem + A.off_e);
   float* e_im = e_re + kTT + 16;
+  float* etile = reinterpret_cast<float*>(smem + A.off_etile);  // [stage][re|im][kTT]
+  float2* snap = reinterpret_cast<float2*>(smem + A.off_snap);
   float2* win = reinterpret_cast<float2*>(smem + A.off_win);
 
   // ---- init: zero the history rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56;
   //      x[<0] = +0 for the matched filter), set up the TMA barriers
   for (int i = threadIdx.x; i < A.bhist_size * (C.mf_rem ? 2 : 1); i += kFusedThreads) bhist[i] = make_float2(0.f, 0.f);
-  for (int i = threadIdx.x; i < A.ahist_size; i += kFusedThreads) ahist[i] = 0.f;
-  for (int i = threadIdx.x; i < A.ycl_size; i += kFusedThreads) ycl[i] = make_float2(0.f, 0.f);
+  if (SPEC) {
+    for (int i = threadIdx.x; i < kTileStages * kTT; i += kFusedThreads) { tile_y[i] = make_float2(0.f, 0.f); tile_a[i] = 0.f; }
+  } else {
+    for (int i = threadIdx.x; i < A.ahist_size; i += kFusedThreads) ahist[i] = 0.f;
+    for (int i = threadIdx.x; i < A.ycl_size; i += kFusedThreads) ycl[i] = make_float2(0.f, 0.f);
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; s++) mbar_init(&B.raw_full[s], 1);
+    mbar_init(&B.win_ready, 1);
+    mbar_init(&B.win_free, 1);
     B.n_ev = 0;
     mbar_fence_init();
   }
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
         issue_tile_load<DECIM>(A, sg, k, raw + (size_t)k * A.raw_stage_samples, &B.raw_full[k]);
     }
     const int bmask = A.bhist_size - 1, amask = A.ahist_size - 1;
-    const float winlen_f = (float)C.win_length;
+    const float winlen_f = (float)C.win_length, dclen_w = (float)C.dc_length;
     PH_DECL
     for (int k = 0; k < ntiles; k++) {
       const int rs = k % kRawStages, ts = k % kTileStages;
@@ -275,18 +302,20 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
         }
       }
       PH_MARK(2)
-      named_bar_sync(BAR_WORKERS, kWorkerThreads);  // raw stage rs fully consumed, block sums visible
+      bar_sync_workers();  // raw stage rs fully consumed, block sums visible
       if (wt == 0 && k + kRawStages < ntiles)
         issue_tile_load<DECIM>(A, sg, k + kRawStages, raw + (size_t)rs * A.raw_stage_samples, &B.raw_full[rs]);
       PH_MARK(3)
-      if (k >= kTileStages) named_bar_sync(BAR_TILE_EMPTY + ts, 96);  // the sequencer is done with tile k - 3
+      if (k >= kTileStages) bar_sync_stage<BAR_TILE_EMPTY>(ts, 96);  // the sequencer is done with tile k - 3
       PH_MARK(4)
       // ---- y[n] = ((P(n-q) + B(n-q+1)) + ...) + B(n);  a = |y|
       float a_reg[kTT / kWorkerThreads];
+      float2 y_reg[kTT / kWorkerThreads];
 #pragma unroll
       for (int r = 0; r < kTT / kWorkerThreads; r++) {
         const int t = wt + r * kWorkerThreads;
         a_reg[r] = 0.f;
+        y_reg[r] = make_float2(0.f, 0.f);
         if (t < nvalid) {
           const int n = k * kTT + t;
           float2 y;
@@ -307,12 +336,13 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
           const float a = cabsf_ref(y.x, y.y);  // gate_impl.cc:130
           tile_y[ts * kTT + t] = y;
           tile_a[ts * kTT + t] = a;
-          ahist[n & amask] = a;
+          if (!SPEC) ahist[n & amask] = a;
           a_reg[r] = a;
+          y_reg[r] = y;
         }
       }
       PH_MARK(5)
-      named_bar_sync(BAR_WORKERS, kWorkerThreads);  // amplitude ring visible
+      bar_sync_workers();  // this tile's amplitudes / filtered samples visible
       PH_MARK(6)
       // ---- (a - win_samples[win_index]) / win_length   (gate_impl.cc:131)
 #pragma unroll
@@ -320,11 +350,25 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
         const int t = wt + r * kWorkerThreads;
         if (t < nvalid) {
           const int n = k * kTT + t;
-          tile_d[ts * kTT + t] = f_div(f_sub(a_reg[r], ahist[(n - C.win_length) & amask]), winlen_f);
+          if (SPEC) {
+            // the tile stages are one time-indexed ring of kTileStages*kTT samples (tile k-1 is still resident)
+            int ia = ts * kTT + t - C.win_length;
+            if (ia < 0) ia += kTileStages * kTT;
+            tile_d[ts * kTT + t] = f_div(f_sub(a_reg[r], tile_a[ia]), winlen_f);
+            // (in - dc_samples[dc_index]) / dc_length assuming the previous dc_length samples were all closed
+            // (gate_impl.cc:141); the sequencer redoes the few samples for which that is not true
+            int iy = ts * kTT + t - C.dc_length;
+            if (iy < 0) iy += kTileStages * kTT;
+            const float2 old = tile_y[iy];
+            etile[(ts * 2 + 0) * kTT + t] = f_div(f_sub(y_reg[r].x, old.x), dclen_w);
+            etile[(ts * 2 + 1) * kTT + t] = f_div(f_sub(y_reg[r].y, old.y), dclen_w);
+          } else {
+            tile_d[ts * kTT + t] = f_div(f_sub(a_reg[r], ahist[(n - C.win_length) & amask]), winlen_f);
+          }
         }
       }
       __threadfence_block();
-      named_bar_arrive(BAR_TILE_FULL + ts, 96);
+      bar_arrive_stage<BAR_TILE_FULL>(ts, 96);
       PH_MARK(7)
     }
     if (wt == 0) { PH_DUMP(8) }
@@ -345,7 +389,8 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
     int n_e = 0;                   // closed samples of the tile whose DC chain is still to run
     // --- emission state (tile k-1)
     bool f_open = false, f_store = false;
-    int f_wpos = 0, pending_free = 0;
+    int f_wpos = 0, n_signalled = 0, n_freed = 0;
+    int closed_since = C.dc_length;  // closed samples since the last window (>= dc_length: ring lookback is time-contiguous)
     float2 dc_open = make_float2(0.f, 0.f);
     const int ymask = A.ycl_size - 1;
     const float dclen_f = (float)C.dc_length;
@@ -357,10 +402,12 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
       const int nvalid = k < ntiles ? min(kTT, n_out - k * kTT) : 0;
       float* davg = tile_d + ts * kTT;
       PH_MARK(0)
-      if (k < ntiles) named_bar_sync(BAR_TILE_FULL + ts, 96);
+      if (k < ntiles) bar_sync_stage<BAR_TILE_FULL>(ts, 96);
       PH_MARK(1)
       // ---- 1. the three recurrences, one pass: avg_ampl over tile k, dc_est over tile k-1's closed samples
-      if (lane < 3) chain_inplace(lane == 0 ? davg : (lane == 1 ? e_re : e_im), lane == 0 ? nvalid : n_e, acc);
+      float* pe_re = SPEC ? etile + (((k + kTileStages - 1) % kTileStages) * 2 + 0) * kTT : e_re;  // tile k-1's list
+      float* pe_im = SPEC ? pe_re + kTT : e_im;
+      if (lane < 3) chain_inplace(lane == 0 ? davg : (lane == 1 ? pe_re : pe_im), lane == 0 ? nvalid : n_e, acc);
       __syncwarp();
       PH_MARK(2)
       // ---- 2. finish tile k-1: window emission (gate_impl.cc:173,187) and hand-off to the decoder
@@ -389,18 +436,18 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
               if (lane == 0) { B.meta_kind = B.ev[e].a; B.meta_ordinal = B.ev[e].b; B.meta_len = B.ev[e].c; B.meta_open = B.ev[e].d; }
               __threadfence_block();
               __syncwarp();
-              named_bar_arrive(BAR_WIN_READY, 64);
-              pending_free++;
+              if (lane == 0) mbar_arrive(&B.win_ready);
+              n_signalled++;
             }
             pos = epos;
           } else if (etype == 1) {
             // READER COMMAND DETECTED (gate_impl.cc:164-180): dc_est right after the trigger sample
             const int j = B.ev[e].a;
-            dc_open = make_float2(e_re[j], e_im[j]);
+            dc_open = make_float2(pe_re[j], pe_im[j]);
             f_store = B.ev[e].c != 0;
             f_open = true;
             if (f_store) {
-              while (pending_free > 0) { named_bar_sync(BAR_WIN_FREE, 64); pending_free--; }  // window buffer free
+              while (n_freed < n_signalled) { mbar_wait(&B.win_free, n_freed & 1); n_freed++; }  // window buffer free
               if (lane == 0) win[0] = c_sub(py[epos], dc_open);
             }
             f_wpos = 1;
@@ -408,10 +455,6 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
           }
         }
         __syncwarp();
-        if (k - 1 + kTileStages < ntiles) {
-          __threadfence_block();
-          named_bar_arrive(BAR_TILE_EMPTY + pts, 96);  // stage of tile k-1 may be refilled
-        }
       }
       PH_MARK(3)
       // ---- 3. thresholds + state machine of tile k; collect its closed samples for the DC chain
@@ -459,13 +502,47 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
             // ---- DC tracker inputs for the closed run [run_start, pos) (gate_impl.cc:141-143); the run
             //      includes the trigger sample, as in the reference (the update precedes the open test)
             const int len = pos - run_start;
-            for (int j = lane; j < len; j += 32) ycl[(n_closed + j) & ymask] = ty[run_start + j];
-            __syncwarp();
-            for (int j = lane; j < len; j += 32) {
-              const float2 yv = ty[run_start + j];
-              const float2 old = ycl[(n_closed + j - C.dc_length) & ymask];
-              e_re[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
-              e_im[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
+            if (SPEC) {
+              float* er = etile + (ts * 2 + 0) * kTT;
+              float* ei = er + kTT;
+              if (run_start == 0 && pos == nvalid && !opened && closed_since >= C.dc_length) {
+                // quiet tile: the workers' differences are exact, nothing to do
+              } else {
+                // rebuild the list for this run: ring lookback = snapshot taken at the last gate opening for
+                // the first dc_length closed samples after a window, else the sample dc_length earlier
+                for (int j = lane; j < len; j += 32) {
+                  const int i = run_start + j, m = closed_since + j;
+                  const float2 yv = ty[i];
+                  float2 old;
+                  if (m < C.dc_length) {
+                    old = snap[m];
+                  } else {
+                    int iy = ts * kTT + i - C.dc_length;
+                    if (iy < 0) iy += kTileStages * kTT;
+                    old = tile_y[iy];
+                  }
+                  er[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
+                  ei[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
+                }
+              }
+              closed_since = min(closed_since + len, 1 << 24);
+              if (opened) {
+                // the dc ring as it stands when the gate opens: the last dc_length closed samples
+                for (int j = lane; j < C.dc_length; j += 32) {
+                  int iy = ts * kTT + (pos - 1) - C.dc_length + 1 + j;
+                  if (iy < 0) iy += kTileStages * kTT;
+                  snap[j] = tile_y[iy];
+                }
+              }
+            } else {
+              for (int j = lane; j < len; j += 32) ycl[(n_closed + j) & ymask] = ty[run_start + j];
+              __syncwarp();
+              for (int j = lane; j < len; j += 32) {
+                const float2 yv = ty[run_start + j];
+                const float2 old = ycl[(n_closed + j - C.dc_length) & ymask];
+                e_re[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
+                e_im[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
+              }
             }
             n_closed += len;
             n_e += len;
@@ -494,6 +571,7 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
               }
               nev++;
               wcount++;
+              closed_since = 0;
               // the Gen2 logic answers (ACK after RN16 -> GATE_SEEK_EPC, Query/QueryRep after EPC ->
               // GATE_SEEK_RN16) and the next gate call applies it (gate_impl.cc:112-123)
               to_ungate = kind ? C.len_rn16 : C.len_epc;
@@ -508,22 +586,27 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
       }
       if (lane == 0) B.n_ev = min(nev, kMaxTileEvents);
       __syncwarp();
+      // the stage of tile k-1 (its samples fed the ring lookbacks / snapshot above) may be refilled now
+      if (k >= 1 && k - 1 + kTileStages < ntiles) {
+        __threadfence_block();
+        bar_arrive_stage<BAR_TILE_EMPTY>((k - 1) % kTileStages, 96);
+      }
       PH_MARK(5)
     }
     PH_DUMP(0)
     // ---- shut the decoder down, publish the window count
-    while (pending_free > 0) { named_bar_sync(BAR_WIN_FREE, 64); pending_free--; }
+    while (n_freed < n_signalled) { mbar_wait(&B.win_free, n_freed & 1); n_freed++; }
     if (lane == 0) {
       B.meta_kind = -1;
       A.counts[seg] = wcount;
     }
     __threadfence_block();
     __syncwarp();
-    named_bar_arrive(BAR_WIN_READY, 64);
+    if (lane == 0) mbar_arrive(&B.win_ready);
   } else {
     // =========================================================== decoder
-    for (;;) {
-      named_bar_sync(BAR_WIN_READY, 64);
+    for (int j = 0;; j++) {
+      while (!mbar_try_wait(&B.win_ready, j & 1)) __nanosleep(400);  // idle most of the time: poll slowly
       const int kind = B.meta_kind;
       if (kind < 0) break;
       const int ordinal = B.meta_ordinal, open_idx = B.meta_open, len = B.meta_len;
@@ -536,7 +619,7 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
         for (int p = lane; p < len; p += 32) tap[p] = win[p];
       }
       __syncwarp();
-      named_bar_arrive(BAR_WIN_FREE, 64);
+      if (lane == 0) mbar_arrive(&B.win_free);
     }
   }
 }
