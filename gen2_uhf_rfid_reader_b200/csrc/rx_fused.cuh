@@ -614,10 +614,12 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
       decode_window_warp(C, kind, win, len, nullptr, wd);
       rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
       if (lane == 0) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
+#ifndef RFID_B200_PHASE_PROFILE
       if (A.window_tap) {
         float2* tap = A.window_tap + ((size_t)seg * A.max_windows + ordinal) * C.len_epc;
         for (int p = lane; p < len; p += 32) tap[p] = win[p];
       }
+#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.win_free);
     }

@@ -297,6 +297,42 @@ __attribute__((visibility("default"))) int gen2flow_run_segments(
   return 0;
 }
 
+/* The reader block alone (no gate / decoder, hence no GPU): drive its state machine through a scripted
+ * inventory -- START, then per round: Query or QueryRep (alternating), ACK with the given 16 RN16 bits,
+ * CW -- and return the TX envelope.  Lets the CPU suite compare this repo's reader block with the
+ * reference's sample for sample. */
+__attribute__((visibility("default"))) int gen2flow_reader_script(const float* rn16_bits, int n_rounds, int dac_rate,
+                                                                   float* tx, size_t tx_cap, size_t* tx_n)
+{
+  initialize_reader_state();
+  reader::sptr R = reader::make(400000, dac_rate);
+  std::vector<float> buf(1 << 16), all;
+  auto step = [&](const float* in, int n_in) {
+    gr_vector_int ni(1, n_in);
+    gr_vector_const_void_star iv(1, (const void*)in);
+    gr_vector_void_star ov(1, (void*)buf.data());
+    int w = R->general_work((int)buf.size(), ni, iv, ov);
+    if (w > 0) all.insert(all.end(), buf.begin(), buf.begin() + w);
+  };
+  step(nullptr, 0); /* START */
+  for (int r = 0; r < n_rounds; r++) {
+    if (r > 0) reader_state->gen2_logic_status = (r & 1) ? SEND_QUERY_REP : SEND_QUERY;
+    step(nullptr, 0); /* Query / QueryRep */
+    step(nullptr, 0); /* IDLE: nothing */
+    reader_state->gen2_logic_status = SEND_ACK;
+    step(rn16_bits + 16 * r, 7);  /* incomplete RN16: must not answer */
+    step(rn16_bits + 16 * r, 16); /* ACK */
+    step(nullptr, 0);             /* CW */
+  }
+  int nq = reader_state->reader_stats.n_queries_sent;
+  size_t c = std::min(tx_cap, all.size());
+  memcpy(tx, all.data(), c * sizeof(float));
+  *tx_n = all.size();
+  delete reader_state;
+  reader_state = nullptr;
+  return nq;
+}
+
 __attribute__((visibility("default"))) void gen2flow_set_logging(int info, int debug)
 {
   gr::block::s_info.enabled = info != 0;

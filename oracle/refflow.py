@@ -44,6 +44,8 @@ class FlowLib:
         L.gen2flow_run_segments.restype = C.c_int
         L.gen2flow_run_segments.argtypes = [f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_int, i32p, C.POINTER(C.c_double)]
+        L.gen2flow_reader_script.restype = C.c_int
+        L.gen2flow_reader_script.argtypes = [f32p, C.c_int, C.c_int, f32p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.gen2flow_is_reference.restype = C.c_int
         L.gen2flow_fixed_q.restype = C.c_int
         L.gen2flow_set_logging.argtypes = [C.c_int, C.c_int]
@@ -87,6 +89,15 @@ class FlowLib:
             out["y"] = y[:2 * (n_raw // decim)].view(np.complex64).copy()
         return out
 
+    def reader_script(self, rn16_bits, dac_rate=1000000):
+        """scripted run of the reader block alone (CPU only): returns (tx envelope, n_queries_sent)"""
+        bits = np.ascontiguousarray(rn16_bits, dtype=np.float32).reshape(-1, 16)
+        tx = np.zeros(bits.shape[0] * 12000 + 8000, dtype=np.float32)
+        n = C.c_size_t(0)
+        nq = self.lib.gen2flow_reader_script(bits.ctypes.data_as(C.POINTER(C.c_float)), bits.shape[0], dac_rate,
+                                             tx.ctypes.data_as(C.POINTER(C.c_float)), tx.size, C.byref(n))
+        return tx[:n.value].copy(), nq
+
     def run_decimated(self, y, fs_dec=400000, dac_rate=1000000, chunk=4096, max_recs=4096):
         yy = np.ascontiguousarray(y, dtype=np.complex64).view(np.float32)
         yy, p = self._f32(yy)
@@ -114,6 +125,14 @@ class FlowLib:
         if rc < 0:
             raise RuntimeError("gen2flow_run_segments failed: %d" % rc)
         return recs, counts, secs.value
+
+
+def B200Flow():
+    """the A/B harness around THIS repo's host blocks (needs a B200 at run time)"""
+    path = os.path.join(HERE, "libgen2flow_b200.so")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path + " (make -C oracle flow_b200)")
+    return FlowLib(path)
 
 
 def RefFlow(fixed_q=0):

@@ -237,3 +237,50 @@ def test_decode_is_idempotent_and_order_independent(rx):
     for f in a.dtype.names:
         if f != "segment":
             assert c[f].tobytes() == a[perm][f].tobytes(), f
+
+
+# ------------------------------------------------------------------ the GNU Radio drop-in blocks, end to end
+def test_flowgraph_through_host_blocks_reproduces_readme(cfg1_iq, cfg1_golden):
+    """apps/reader.py's offline graph with THIS repo's gate / tag_decoder / reader blocks (thin hosts over the
+    C-ABI, GPU underneath) under the oracle's scheduler: README block, records and TX commands as the reference"""
+    import re
+    import sys
+    from oracle import refflow
+    F = refflow.B200Flow()
+    assert not F.is_reference
+    r = F.run_stream(cfg1_iq, want_tx=True)
+    t = r["text"]
+    for pat, val in ((r"queryreps sent : (\d+)", 71), (r"Inventory round : (\d+)", 72), (r"decoded EPC : (\d+)", 70),
+                     (r"unique tags : (\d+)", 1), (r"Num of reads : (\d+)", 70)):
+        assert int(re.search(pat, t).group(1)) == val, t
+    assert "Tag ID : 27" in t
+    assert r["n_windows"] == 142
+    _assert_same(r["records"], cfg1_golden, "host blocks")
+    sys.path.insert(0, GOLDEN)
+    from make_golden import decode_pie
+    cmds = decode_pie(r["tx"])
+    gold = json.load(open(os.path.join(GOLDEN, "file_sink_commands.json")))
+    assert [b for k, b in cmds if k == "preamble"][:72] == gold["queries"]
+    assert [b for k, b in cmds if k == "framesync"][:71] == gold["acks"]
+    # chunk-size independent, like the reference
+    r2 = F.run_stream(cfg1_iq[:400000], chunk=257)
+    r3 = F.run_stream(cfg1_iq[:400000], chunk=50000)
+    assert r2["records"].tobytes() == r3["records"].tobytes()
+
+
+# ------------------------------------------------------------------ rate sweep (BASELINE.json configs[4])
+@pytest.mark.parametrize("adc,ntaps", [(1000000, 12), (1000000, 13), (2000000, 20), (4000000, 50), (6000000, 75), (8000000, 100)])
+def test_rate_sweep_bit_exact(adc, ntaps):
+    """other sample rates / tap counts: generic block-sum path (partial blocks at 12/13 taps) and the
+    long-ring kernel variant above 5 MS/s"""
+    from gen2_uhf_rfid_reader_b200 import capi
+    from oracle.pyoracle import Oracle
+    rxr = capi.Gen2Rx(adc_rate=adc, ntaps=ntaps)
+    O = Oracle(adc_rate=adc, ntaps=ntaps)
+    cap = synth.make_capture(20, seed=4, adc_rate=adc)
+    iq = cap["iq"].numpy()
+    recs, counts = rxr.decode_capture_host(iq, cap["segments"], max_windows=4)
+    orecs, ocounts, _ = O.decode_segments(iq, cap["segments"], max_per_seg=4)
+    assert counts.tolist() == ocounts.tolist()
+    _assert_same(recs, orecs, "adc %d ntaps %d" % (adc, ntaps))
+    assert counts.sum() >= 20

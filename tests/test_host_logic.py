@@ -93,3 +93,28 @@ def test_gather_records_world2_gloo():
     assert np.frombuffer(cnt_b, dtype=np.int32).tolist() == counts.tolist()
     for f in recs.dtype.names:
         assert got[f].tobytes() == recs[f].tobytes(), f
+
+
+def test_reader_block_matches_reference_sample_for_sample(ref_flow):
+    """this repo's reader block (Gen2 logic + PIE generator, host C++) vs the reference's, scripted on CPU:
+    START, Query/QueryRep alternating, ACK(RN16), CW -- identical TX envelope and query count"""
+    from oracle import refflow
+    try:
+        mine = refflow.B200Flow()
+    except FileNotFoundError:
+        pytest.skip("oracle/libgen2flow_b200.so not built")
+    bits = np.random.default_rng(3).integers(0, 2, size=(9, 16)).astype(np.float32)
+    a, na = ref_flow.reader_script(bits)
+    b, nb = mine.reader_script(bits)
+    assert na == nb == 9
+    assert a.size == b.size and np.array_equal(a, b)
+    # and the Query it sends is the one in the reference author's TX capture
+    import json
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from make_golden import decode_pie
+    cmds = decode_pie(b)
+    gold = json.load(open(os.path.join(GOLDEN, "file_sink_commands.json")))
+    assert [c for k, c in cmds if k == "preamble"][0] == gold["queries"][0]
+    acks = [c for k, c in cmds if k == "framesync" and len(c) == 18]
+    assert acks[0] == "01" + "".join(str(int(x)) for x in bits[0])
