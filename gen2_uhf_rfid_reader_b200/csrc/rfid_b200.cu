@@ -37,6 +37,7 @@ struct rfid_b200_ctx {
   void* d_segs; size_t d_segs_bytes;
   void* d_res; size_t d_res_bytes;
   void* d_cnt; size_t d_cnt_bytes;
+  void* d_win; size_t d_win_bytes;  // per-segment window scratch of the fused kernel
   // block mode
   GateState* d_gate;
   GateCallOut* d_gate_out;
@@ -129,7 +130,8 @@ void make_layout(const RxConfig& c, FusedArgs& L)
     L.off_ycl = off; off = align_up(off + L.ycl_size * 8, 16);
     L.off_e = off; off += 2 * (kTT + 16) * 4;
   }
-  L.off_win = off; off = align_up(off + c.len_epc * 8, 16);
+  L.rn16_pad = align_up(c.len_rn16, 16);
+  L.win_stride = L.rn16_pad + align_up(c.len_epc, 16);
   L.smem_bytes = off;
 }
 
@@ -214,6 +216,7 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
   ctx->params = *p; ctx->cfg = cfg; ctx->device = p->device;
   ctx->window_tap = nullptr; ctx->last_launches = 0; ctx->timing = false; ctx->kernel_ms = 0.f; ctx->kernel_launches = 0;
   ctx->d_iq = ctx->d_segs = ctx->d_res = ctx->d_cnt = ctx->d_in = ctx->d_out = ctx->d_m2 = ctx->d_mf = nullptr;
+  ctx->d_win = nullptr; ctx->d_win_bytes = 0;
   ctx->d_iq_bytes = ctx->d_segs_bytes = ctx->d_res_bytes = ctx->d_cnt_bytes = ctx->d_in_bytes = ctx->d_out_bytes = ctx->d_m2_bytes = ctx->d_mf_bytes = 0;
   ctx->d_gate = nullptr; ctx->d_gate_out = nullptr; ctx->d_one = nullptr;
   ctx->mf_abs0 = 0; ctx->mf_have = 0; ctx->mf_next_n = 0;
@@ -255,7 +258,7 @@ void rfid_b200_destroy(rfid_b200_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   drain_timing(ctx);
-  void* ptrs[] = {ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
+  void* ptrs[] = {ctx->d_win, ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
                   ctx->d_gate, ctx->d_gate_out, ctx->d_one};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -311,6 +314,13 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;  // NULL = the (legacy) default stream, as documented
   FusedArgs A = ctx->layout;
+  {
+    // window scratch: one RN16 + one EPC window per segment (grown on demand; cudaMalloc synchronises, so a
+    // caller that wants a fully asynchronous call sizes the context once with its largest batch)
+    int rc = grow(ctx, &ctx->d_win, &ctx->d_win_bytes, (size_t)nseg * A.win_stride * sizeof(float2));
+    if (rc) return rc;
+  }
+  A.win_scratch = reinterpret_cast<float2*>(ctx->d_win);
   A.iq = reinterpret_cast<const float2*>(d_iq);
   A.n_raw = n_raw;
   A.segs = d_segs;

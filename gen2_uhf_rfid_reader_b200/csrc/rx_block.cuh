@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(32) decode_block_kernel(RxConfig C, int kind, 
   for (int i = threadIdx.x; i < n; i += 32) w[i] = win_g[i];
   __syncwarp();
   WindowDecode wd;
-  decode_window_warp(C, kind, w, n, M, wd);
+  decode_window_warp<false>(C, kind, w, n, M, wd);
   if (threadIdx.x == 0)
     store_result(res, wd, 0, 0, 0, kind == RFID_B200_RN16 ? C.len_rn16 : C.len_epc, kind);
 }

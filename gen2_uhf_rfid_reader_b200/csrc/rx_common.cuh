@@ -106,10 +106,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
       : "memory");
   return ok != 0;
 }
+// spin a few times (the phase is usually complete or about to be), then back off so that a waiting warp
+// does not take issue slots away from the latency-critical warps of the co-resident CTAs
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  for (int i = 0; i < 4; i++)
+    if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(200);
 }
 // wait for a phase that is not on this warp's critical path: let the hardware park the warp
 // (suspend-time hint, ns) instead of burning issue slots that the sequencer warps need

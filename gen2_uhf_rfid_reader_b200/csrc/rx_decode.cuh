@@ -49,9 +49,19 @@ __device__ __forceinline__ int crc16_check(const uint32_t bits[4])
 // w: window samples (y - dc_est), n_avail samples; M: scratch for |w|^2 (EPC only, >= n_avail floats).
 // All 32 lanes of the warp must call; the result is valid in every lane.
 // M == nullptr: |w|^2 is evaluated at every gather of the period search instead of being staged.
-__device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, const float2* __restrict__ w,
+// GLOBAL_W: the window lives in global memory (L2-resident scratch written by another warp of this CTA):
+// read it with ld.global.cg so that no stale L1 line can be observed.
+template <bool GLOBAL_W>
+struct WinView {
+  const float2* p;
+  __device__ __forceinline__ float2 operator[](int i) const { return GLOBAL_W ? __ldcg(p + i) : p[i]; }
+};
+
+template <bool GLOBAL_W>
+__device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, const float2* __restrict__ w_ptr,
                                                    int n_avail, float* __restrict__ M, WindowDecode& out)
 {
+  const WinView<GLOBAL_W> w{w_ptr};
   const int lane = threadIdx.x & 31;
   const float n = c.n_tag_bit_f;
 
@@ -154,7 +164,7 @@ __device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, 
   if (lane < number_steps) {
     const float Tt = f_add(min_val, f_div(f_mul((float)lane, f_sub(max_val, min_val)), (float)(number_steps - 1)));
     float e = 0.0f;
-#pragma unroll 4
+#pragma unroll 16
     for (int i = 0; i < 256; i++) {
       int p = (int)f_add(f_mul((float)i, Tt), (float)index);  // :161
       e = f_add(e, M ? M[p] : c_norm(w[p]));

@@ -83,6 +83,8 @@ struct FusedArgs {
   rfid_b200_window_result* results;
   int32_t* counts;
   float2* window_tap;            // optional: ungated samples of every stored window (stride len_epc)
+  float2* win_scratch;           // [nseg][win_stride]: the window being decoded (RN16 at 0, EPC at rn16_pad); L2-resident
+  int win_stride, rn16_pad;
   RxConfig cfg;
   // shared-memory carve-up (bytes from the dynamic smem base), computed on the host
   int off_raw, raw_stage_samples;
@@ -93,7 +95,6 @@ struct FusedArgs {
   int off_e;                     // float[2][kTT + 16]                      (generic path)
   int off_etile;                 // float[kTileStages][2][kTT] (+pad)       (fast path: workers' DC-ring differences)
   int off_snap;                  // float2[dc_length]: dc ring snapshot taken when the gate opens (fast path)
-  int off_win;
   int smem_bytes;
 };
 
@@ -106,8 +107,8 @@ struct TileEvent {
 
 struct FusedShared {
   uint64_t raw_full[kRawStages];
-  uint64_t win_ready, win_free;
-  int meta_kind, meta_open, meta_ordinal, meta_len;
+  uint64_t win_ready[2], win_free[2];  // alternate per hand-off: the sequencer may run two hand-offs ahead
+  int meta_kind[2], meta_open[2], meta_ordinal[2], meta_len[2];  // double-buffered by hand-off parity
   int n_ev;
   TileEvent ev[kMaxTileEvents];
 };
@@ -205,7 +206,7 @@ __device__ __forceinline__ void issue_tile_load(const FusedArgs& A, const rfid_b
 // come straight from the time-indexed tile stages and the workers pre-compute the DC-ring differences, so
 // on a tile without gate activity the sequencer only runs its running sums.
 template <int DECIM, int MFQ, bool SPEC>
-__global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs A)
+__global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedArgs A)
 {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ FusedShared B;
@@ -230,7 +231,9 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
   float* e_im = e_re + kTT + 16;
   float* etile = reinterpret_cast<float*>(smem + A.off_etile);  // [stage][re|im][kTT]
   float2* snap = reinterpret_cast<float2*>(smem + A.off_snap);
-  float2* win = reinterpret_cast<float2*>(smem + A.off_win);
+  // ungated window samples go to a per-segment global scratch (written once, read once by the decoder warp
+  // of the same CTA a few microseconds later: L2 traffic, not shared memory -- that is what lets 8 CTAs fit an SM)
+  float2* const win_base = A.win_scratch + (size_t)seg * A.win_stride;
 
   // ---- init: zero the history rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56;
   //      x[<0] = +0 for the matched filter), set up the TMA barriers
@@ -243,8 +246,7 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; s++) mbar_init(&B.raw_full[s], 1);
-    mbar_init(&B.win_ready, 1);
-    mbar_init(&B.win_free, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&B.win_ready[s], 1); mbar_init(&B.win_free[s], 1); }
     B.n_ev = 0;
     mbar_fence_init();
   }
@@ -390,6 +392,7 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
     // --- emission state (tile k-1)
     bool f_open = false, f_store = false;
     int f_wpos = 0, n_signalled = 0, n_freed = 0;
+    float2* win = win_base;
     int closed_since = C.dc_length;  // closed samples since the last window (>= dc_length: ring lookback is time-contiguous)
     float2 dc_open = make_float2(0.f, 0.f);
     const int ymask = A.ycl_size - 1;
@@ -433,10 +436,13 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
             f_open = false;
             if (f_store) {
               __syncwarp();
-              if (lane == 0) { B.meta_kind = B.ev[e].a; B.meta_ordinal = B.ev[e].b; B.meta_len = B.ev[e].c; B.meta_open = B.ev[e].d; }
-              __threadfence_block();
+              if (lane == 0) {
+                const int ms = n_signalled & 1;  // the slot of hand-off n-2 is free: at most one window is outstanding
+                B.meta_kind[ms] = B.ev[e].a; B.meta_ordinal[ms] = B.ev[e].b; B.meta_len[ms] = B.ev[e].c; B.meta_open[ms] = B.ev[e].d;
+              }
+              __threadfence();  // window samples were written to global memory
               __syncwarp();
-              if (lane == 0) mbar_arrive(&B.win_ready);
+              if (lane == 0) mbar_arrive(&B.win_ready[n_signalled & 1]);
               n_signalled++;
             }
             pos = epos;
@@ -446,8 +452,10 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
             dc_open = make_float2(pe_re[j], pe_im[j]);
             f_store = B.ev[e].c != 0;
             f_open = true;
+            win = win_base + (B.ev[e].d ? A.rn16_pad : 0);  // RN16 and EPC windows have their own scratch areas
             if (f_store) {
-              while (n_freed < n_signalled) { mbar_wait(&B.win_free, n_freed & 1); n_freed++; }  // window buffer free
+              // the area is reused two windows later: at most one window may still be with the decoder
+              while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
               if (lane == 0) win[0] = c_sub(py[epos], dc_open);
             }
             f_wpos = 1;
@@ -552,7 +560,7 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
               cur_store = wcount < A.max_windows;
               if (lane == 0 && nev < kMaxTileEvents) {
                 TileEvent& ev = B.ev[nev];
-                ev.type = 1; ev.pos = pos - 1; ev.a = n_e - 1; ev.b = open_idx; ev.c = cur_store ? 1 : 0; ev.d = 0;
+                ev.type = 1; ev.pos = pos - 1; ev.a = n_e - 1; ev.b = open_idx; ev.c = cur_store ? 1 : 0; ev.d = wcount & 1;
               }
               nev++;
               num_pulses = 0;
@@ -595,33 +603,35 @@ __global__ void __launch_bounds__(kFusedThreads) rx_fused_kernel(const FusedArgs
     }
     PH_DUMP(0)
     // ---- shut the decoder down, publish the window count
-    while (n_freed < n_signalled) { mbar_wait(&B.win_free, n_freed & 1); n_freed++; }
+    // the exit message needs the meta slot of hand-off n-2 only
+    while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
     if (lane == 0) {
-      B.meta_kind = -1;
+      B.meta_kind[n_signalled & 1] = -1;
       A.counts[seg] = wcount;
     }
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&B.win_ready);
+    if (lane == 0) mbar_arrive(&B.win_ready[n_signalled & 1]);
   } else {
     // =========================================================== decoder
     for (int j = 0;; j++) {
-      while (!mbar_try_wait(&B.win_ready, j & 1)) __nanosleep(400);  // idle most of the time: poll slowly
-      const int kind = B.meta_kind;
+      while (!mbar_try_wait(&B.win_ready[j & 1], (j >> 1) & 1)) __nanosleep(400);  // idle most of the time: poll slowly
+      const int kind = B.meta_kind[j & 1];
       if (kind < 0) break;
-      const int ordinal = B.meta_ordinal, open_idx = B.meta_open, len = B.meta_len;
+      const int ordinal = B.meta_ordinal[j & 1], open_idx = B.meta_open[j & 1], len = B.meta_len[j & 1];
       WindowDecode wd;
-      decode_window_warp(C, kind, win, len, nullptr, wd);
+      const float2* win = win_base + (kind ? A.rn16_pad : 0);
+      decode_window_warp<true>(C, kind, win, len, nullptr, wd);
       rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
       if (lane == 0) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
 #ifndef RFID_B200_PHASE_PROFILE
       if (A.window_tap) {
         float2* tap = A.window_tap + ((size_t)seg * A.max_windows + ordinal) * C.len_epc;
-        for (int p = lane; p < len; p += 32) tap[p] = win[p];
+        for (int p = lane; p < len; p += 32) tap[p] = __ldcg(win + p);
       }
 #endif
       __syncwarp();
-      if (lane == 0) mbar_arrive(&B.win_free);
+      if (lane == 0) mbar_arrive(&B.win_free[j & 1]);
     }
   }
 }
