@@ -14,6 +14,7 @@
 #include "rx_block.cuh"
 #include "rx_common.cuh"
 #include "rx_fused.cuh"
+#include "rx_fused_split.cuh"
 
 using namespace rfid_b200;
 
@@ -107,9 +108,33 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 bool fast_path_ok(const RxConfig& c) { return c.win_length <= kTT && c.dc_length <= kTT; }
 
+// shared-memory carve-up of rx_fused_split_kernel: five tile stages forming one time-indexed ring
+void make_layout_split(const RxConfig& c, FusedArgs& L)
+{
+  int off = 0;
+  L.raw_stage_samples = c.decim * kTT + 2;
+  L.off_raw = off; off = align_up(off + kRawStages * L.raw_stage_samples * 8, 16);
+  L.bhist_size = next_pow2(kTT + c.mf_q + 2);
+  L.off_bhist = off; off = align_up(off + L.bhist_size * 8 * (c.mf_rem ? 2 : 1), 16);
+  L.off_tile_y = off; off += kRing * 8;
+  L.off_tile_a = off; off += kRing * 4;
+  L.off_tile_d = off; off += kRing * 4 + 64;          // + read-ahead pad of the running-sum loop
+  L.off_etile = off; off += kS * 2 * kTT * 4 + 64;
+  L.off_snap = off; off = align_up(off + c.dc_length * 8, 16);
+  L.dstage_samples = decode_stage_samples(c.n_tag_bit_f);
+  if (L.dstage_samples < c.len_rn16) L.dstage_samples = align_up(c.len_rn16, 8);  // an RN16 window is staged whole
+  L.off_dstage = off; off = align_up(off + L.dstage_samples * 8, 16);
+  L.ahist_size = L.ycl_size = 0;
+  L.off_ahist = L.off_ycl = L.off_e = 0;
+  L.rn16_pad = align_up(c.len_rn16, 16);
+  L.win_stride = L.rn16_pad + align_up(c.len_epc, 16);
+  L.smem_bytes = off;
+}
+
 void make_layout(const RxConfig& c, FusedArgs& L)
 {
-  const bool spec = fast_path_ok(c);
+  if (fast_path_ok(c)) { make_layout_split(c, L); return; }
+  const bool spec = false;
   int off = 0;
   L.raw_stage_samples = c.decim * kTT + 2;
   L.off_raw = off; off = align_up(off + kRawStages * L.raw_stage_samples * 8, 16);
@@ -140,8 +165,8 @@ fused_fn pick_kernel(const RxConfig& c)
 {
   if (c.decim != 5) return nullptr;
   if (fast_path_ok(c)) {
-    if (c.mf_rem == 0 && c.mf_q == 5) return rx_fused_kernel<5, 5, true>;  // the reference configuration: 25 taps
-    return rx_fused_kernel<5, 0, true>;
+    if (c.mf_rem == 0 && c.mf_q == 5) return rx_fused_split_kernel<5, 5>;  // the reference configuration: 25 taps
+    return rx_fused_split_kernel<5, 0>;
   }
   return rx_fused_kernel<5, 0, false>;  // long rings (raw rates above 5 MS/s) and any tap count
 }
@@ -336,7 +361,7 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, s));
   }
-  fn<<<nseg, kFusedThreads, A.smem_bytes, s>>>(A);
+  fn<<<nseg, fast_path_ok(ctx->cfg) ? kSplitThreads : kFusedThreads, A.smem_bytes, s>>>(A);
   CK(cudaGetLastError());
   if (ctx->timing) {
     CK(cudaEventRecord(e1, s));

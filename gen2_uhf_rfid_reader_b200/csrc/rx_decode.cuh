@@ -201,6 +201,158 @@ __device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, 
   out.tag_id = (int)((out.bits[3] >> 16) & 0xFFu);  // byte 13 = bits[104..111] (:348-352)
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Staged variant for a window that lives in global memory (the fused kernel's L2-resident scratch): the warp
+// copies the part of the window it is about to use into a small shared-memory stage with coalesced loads and
+// runs the same arithmetic as decode_window_warp from there.  stage_cap >= decode_stage_samples(n_tag_bit).
+__host__ __device__ inline int decode_stage_samples(float n_tag_bit)
+{
+  // one chunk = 32 consecutive bit pairs: 31 symbols + one half symbol at the longest candidate period, + slack
+  return ((int)(32.5f * n_tag_bit * 1.0101f) + 16 + 7) & ~7;
+}
+
+__device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail)
+{
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  for (int p = lane; p < count; p += 32) {
+    const int g = lo + p;
+    stage[p] = (g >= 0 && g < n_avail) ? __ldcg(gw + g) : make_float2(0.f, 0.f);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
+                                                     float2* __restrict__ stage, int stage_cap, WindowDecode& out)
+{
+  const int lane = threadIdx.x & 31;
+  const float n = c.n_tag_bit_f;
+  const float half = f_div(n, 2.0f);
+
+  // ---- tag_sync + h_est need w[0 .. sync_range + 5.5 n): one stage fill (an RN16 window fits entirely)
+  const int head = min(stage_cap, kind == RFID_B200_RN16 ? n_avail : (int)(c.sync_range + 6.0f * n) + 2);
+  stage_fill(stage, gw, 0, head, n_avail);
+  float best = -1.0f;
+  int best_i = 0x7fffffff;
+  for (int i = lane; i < c.sync_range; i += 32) {
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int j = 0; j < 2 * kTagPreambleBits; j++) {
+      int k = (int)f_add((float)i, f_div(f_mul((float)j, n), 2.0f));
+      float2 s = stage[k];
+      float cr = (float)((kPreambleMask >> j) & 1u);
+      float pr = f_sub(f_mul(s.x, cr), f_mul(s.y, 0.0f));
+      float pi = f_add(f_mul(s.x, 0.0f), f_mul(s.y, cr));
+      acc.x = f_add(acc.x, pr);
+      acc.y = f_add(acc.y, pi);
+    }
+    float corr = c_norm(acc);
+    if (corr > best) { best = corr; best_i = i; }
+  }
+  warp_argmax_first(best, best_i);
+  int max_index = 0;
+  float max_corr = 0.0f;
+  if (best > 0.0f) { max_index = best_i; max_corr = best; }
+  {
+    int t1 = (int)f_add((float)max_index, half);
+    int t3 = (int)f_add((float)max_index, f_div(f_mul(3.0f, n), 2.0f));
+    int t6 = (int)f_add((float)max_index, f_div(f_mul(6.0f, n), 2.0f));
+    int t10 = (int)f_add((float)max_index, f_div(f_mul(10.0f, n), 2.0f));
+    int t11 = (int)f_add((float)max_index, f_div(f_mul(11.0f, n), 2.0f));
+    float2 s = stage[max_index];
+    s = c_add(s, stage[t1]);
+    s = c_add(s, stage[t3]);
+    s = c_add(s, stage[t6]);
+    s = c_add(s, stage[t10]);
+    s = c_add(s, stage[t11]);
+    out.h = make_float2(f_div(s.x, 6.0f), f_div(s.y, 6.0f));
+  }
+  out.sync_index = max_index;
+  out.score = max_corr;
+  const int index = (int)f_add(f_add((float)max_index, f_mul((float)kTagPreambleBits, n)), half);
+  const float2 h = out.h;
+  out.bits[0] = out.bits[1] = out.bits[2] = out.bits[3] = 0u;
+
+  if (kind == RFID_B200_RN16) {
+    float jm = (float)index;
+    for (int m = 0; m < lane; m++) jm = f_add(jm, half);
+    bool have = jm < (float)n_avail;
+    unsigned have_mask = __ballot_sync(0xffffffffu, have);
+    float2 s = make_float2(0.0f, 0.0f);
+    if (have) {
+      const int k = (int)roundf(jm);
+      s = k < head ? stage[k] : __ldcg(gw + k);
+    }
+    out.T = 0.0f;
+    out.crc_ok = -1;
+    if (have_mask == 0xffffffffu) {
+      float2 s_next = make_float2(__shfl_down_sync(0xffffffffu, s.x, 1), __shfl_down_sync(0xffffffffu, s.y, 1));
+      float res = c_proj(s, s_next, h);
+      unsigned pos = __ballot_sync(0xffffffffu, res > 0.0f);
+      unsigned S = 0;
+#pragma unroll
+      for (int j = 0; j < 16; j++) S |= ((pos >> (2 * j)) & 1u) << j;
+      unsigned Bv = (S ^ ((S << 1) | 1u)) & 0xFFFFu;
+      unsigned msb = 0;
+#pragma unroll
+      for (int j = 0; j < 16; j++) msb |= ((Bv >> j) & 1u) << (31 - j);
+      out.bits[0] = msb;
+      out.tag_id = (int)(msb >> 16);
+    } else {
+      out.crc_ok = -2;
+      out.tag_id = -1;
+    }
+    return;
+  }
+
+  // ---- symbol-period search (:151-165), 32 steps per stage fill
+  const int number_steps = 20;
+  const float min_val = c.t_min, max_val = c.t_max;
+  const float Tt = f_add(min_val, f_div(f_mul((float)(lane < number_steps ? lane : 0), f_sub(max_val, min_val)), (float)(number_steps - 1)));
+  float e = 0.0f;
+  for (int i0 = 0; i0 < 256; i0 += 32) {
+    const int lo = (int)f_add(f_mul((float)i0, min_val), (float)index);  // smallest index any candidate touches
+    stage_fill(stage, gw, lo, min(stage_cap, (int)(32.0f * max_val + 256.0f * (max_val - min_val)) + 8), n_avail);
+    if (lane < number_steps) {
+#pragma unroll 8
+      for (int i = i0; i < i0 + 32; i++) {
+        int p = (int)f_add(f_mul((float)i, Tt), (float)index);  // :161
+        e = f_add(e, c_norm(stage[p - lo]));
+      }
+    }
+  }
+  float energy = lane < number_steps ? e : -1.0f;
+  int e_idx = lane < number_steps ? lane : 0x7fffffff;
+  warp_argmax_first(energy, e_idx);
+  const int index_T = e_idx;
+  const float T = f_add(min_val, f_div(f_mul((float)index_T, f_sub(max_val, min_val)), (float)(number_steps - 1)));
+  out.T = T;
+  // ---- 128 bit decisions (:171-191), 32 pairs per stage fill
+  const float twoT = f_mul(2.0f, T);
+  unsigned S[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int j0 = r * 32;
+    const int lo = (int)f_add(f_mul((float)j0, twoT), (float)index);
+    stage_fill(stage, gw, lo, stage_cap, n_avail);
+    int j = j0 + lane;
+    int a = (int)f_add(f_mul((float)j, twoT), (float)index);
+    int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);
+    float res = c_proj(stage[a - lo], stage[b - lo], h);
+    S[r] = __ballot_sync(0xffffffffu, res > 0.0f);
+  }
+  unsigned carry = 1u;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    unsigned prev = (S[r] << 1) | carry;
+    carry = S[r] >> 31;
+    unsigned Bv = S[r] ^ prev;
+    out.bits[r] = __brev(Bv);
+  }
+  out.crc_ok = crc16_check(out.bits);
+  out.tag_id = (int)((out.bits[3] >> 16) & 0xFFu);
+}
+
 __device__ __forceinline__ void store_result(rfid_b200_window_result* dst, const WindowDecode& d, int segment, int window,
                                              int open_index, int length, int kind)
 {

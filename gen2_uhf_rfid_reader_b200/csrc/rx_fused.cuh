@@ -33,7 +33,7 @@ namespace rfid_b200 {
 // developer aid: per-phase clock64() sums of the sequencer / worker warp of CTA 0..N, written to the window tap
 #define PH_DECL long long ph_t0 = clock64(), ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PH_MARK(i) { long long ph_t1 = clock64(); ph_acc[i] += ph_t1 - ph_t0; ph_t0 = ph_t1; }
-#define PH_DUMP(base) if (lane == 0 && A.window_tap) { long long* o = reinterpret_cast<long long*>(A.window_tap) + (size_t)blockIdx.x * 16 + (base); for (int i = 0; i < 8; i++) o[i] = ph_acc[i]; }
+#define PH_DUMP(base) if (lane == 0 && A.window_tap) { long long* o = reinterpret_cast<long long*>(A.window_tap) + (size_t)blockIdx.x * 24 + (base); for (int i = 0; i < 8; i++) o[i] = ph_acc[i]; }
 #else
 #define PH_DECL
 #define PH_MARK(i)
@@ -85,6 +85,7 @@ struct FusedArgs {
   float2* window_tap;            // optional: ungated samples of every stored window (stride len_epc)
   float2* win_scratch;           // [nseg][win_stride]: the window being decoded (RN16 at 0, EPC at rn16_pad); L2-resident
   int win_stride, rn16_pad;
+  int off_dstage, dstage_samples; // decoder staging buffer (split kernel)
   RxConfig cfg;
   // shared-memory carve-up (bytes from the dynamic smem base), computed on the host
   int off_raw, raw_stage_samples;

@@ -1,0 +1,571 @@
+// rx_fused_split.cuh -- fast-path variant of the fused capture kernel (reference configuration and every
+// rate whose amplitude / DC rings fit one tile, i.e. raw rates up to 5 MS/s).
+//
+// Same arithmetic as rx_fused.cuh, different schedule.  The order-dependent work of a segment is split over
+// TWO warps that run concurrently, one tile apart:
+//   chain    ONLY the three float running sums (lane 0: avg_ampl over tile i, gate_impl.cc:131; lanes 1,2:
+//            dc_est.re/.im over the closed samples of tile i-2, gate_impl.cc:141).  This is the irreducible
+//            serial part of exact replay: ~5.6 cycles per sample, nothing else on its critical path.
+//   control  thresholds (ballot into 128-bit masks), the edge/pulse state machine by bit-mask hopping, the few
+//            DC-ring differences that the workers could not pre-compute (tiles with gate activity), window
+//            emission to the L2-resident scratch two tiles later (when dc_est at the trigger is known), window
+//            hand-off to the decoder.
+// plus the two workers (TMA wait, block-sum matched filter, exact |y|, ring differences) and the decoder warp.
+// CTA = 5 warps; tile stages form a time-indexed ring of 5 x 128 samples.  All hand-offs are mbarriers
+// (phase = use count of the stage); waits that are not on the chain<->control critical path back off.
+#pragma once
+
+#include "rx_fused.cuh"
+
+namespace rfid_b200 {
+
+constexpr int kS = 5;                         // tile stages
+constexpr int kSplitThreads = 32 * 5;
+constexpr int kRing = kS * kTT;               // time-indexed ring length (samples)
+
+struct SplitShared {
+  uint64_t raw_full[kRawStages];
+  uint64_t tile_full[kS];    // workers (2 arrivals)  -> chain
+  uint64_t chain_done[kS];   // chain   (1)           -> control   (avg of tile i, dc of tile i-2)
+  uint64_t elist_ready[kS];  // control (1)           -> chain     (closed-sample list of tile i final)
+  uint64_t tile_free[kS];    // control (1)           -> workers
+  uint64_t win_ready[2], win_free[2];
+  int meta_kind[2], meta_open[2], meta_ordinal[2], meta_len[2];
+  int n_e[kS];               // closed samples in the DC list of each stage
+  int n_ev[kS];
+  TileEvent ev[kS][kMaxTileEvents];
+};
+
+// a wait that is off the critical path: poll rarely
+__device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity)
+{
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(250);
+}
+// a wait on the critical path: poll back to back
+__device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity)
+{
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---- the edge/pulse state machine of one closed run, warp-parallel -------------------------------------
+// The reference walks the samples one by one (gate_impl.cc:145-180):
+//     n_samples++;  POS && a<thr -> NEG, n_samples=0;   NEG && a>thr -> POS, pulse bookkeeping, n_samples=0;
+//     open when n_samples > T1 && POS && num_pulses > 5.
+// Here: (1) the POS/NEG state before every position follows from the fall-wish / rise-wish masks by a carry
+// chain -- state' = rise | (keep & state) is the carry recurrence of a binary addition, so one 128-bit add gives
+// all 128 states; (2) the resulting edges (<= 32 per batch) are handled one per lane: pulse widths by a shuffle,
+// the run-length of consecutive valid pulses by ballot + popc, the first position at which the gate opens by
+// ballot + ffs.  Exactly the reference's decisions, O(1) warp steps per tile instead of one step per edge.
+struct GateFsm {
+  bool sig_pos;
+  int n_samples, num_pulses;
+};
+
+__device__ __forceinline__ int kth_set_bit128(const unsigned w[4], int k)
+{
+  const int c0 = __popc(w[0]), c1 = c0 + __popc(w[1]), c2 = c1 + __popc(w[2]);
+  int word = 0, r = k;
+  unsigned sel = w[0];
+  if (k >= c2) { word = 3; r = k - c2; sel = w[3]; }
+  else if (k >= c1) { word = 2; r = k - c1; sel = w[2]; }
+  else if (k >= c0) { word = 1; r = k - c0; sel = w[1]; }
+  return 32 * word + (int)__fns(sel, 0, r + 1);
+}
+
+// Processes the closed samples [from, nvalid) of a tile.  Returns the position at which the gate opens
+// (the trigger sample, state updated for the open gate) or -1 (state advanced to the end of the tile).
+__device__ __forceinline__ int fsm_closed_run(const unsigned lt[4], const unsigned gt[4], int from, int nvalid, int n_T1,
+                                              int half_pw, GateFsm& st)
+{
+  const int lane = threadIdx.x & 31;
+  // ---- states by carry propagation: A = rise|keep, B = rise, carry-in = current state
+  unsigned F[4], R[4], X[4];
+  unsigned carry = st.sig_pos ? 1u : 0u;
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    // positions before `from` keep the state (they belong to an earlier run / an open window)
+    const int lo = from - 32 * w;
+    const unsigned live = lo <= 0 ? 0xffffffffu : (lo >= 32 ? 0u : (0xffffffffu << lo));
+    F[w] = lt[w] & live;
+    R[w] = gt[w] & live;
+    const unsigned Pk = ~(F[w] | R[w]);
+    const unsigned Aw = R[w] | Pk, Bw = R[w];
+    const unsigned long long sum = (unsigned long long)Aw + Bw + carry;
+    X[w] = Pk ^ (unsigned)sum;  // carry INTO each bit = state before that position (A ^ B == keep)
+    carry = (unsigned)(sum >> 32);
+  }
+  unsigned E[4], RS[4];
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    RS[w] = ~X[w] & R[w];          // NEG -> POS
+    E[w] = (X[w] & F[w]) | RS[w];  // POS -> NEG, or rise
+  }
+  int pos = from;
+  int remaining = __popc(E[0]) + __popc(E[1]) + __popc(E[2]) + __popc(E[3]);
+  int done = 0;
+  while (true) {
+    const int nb = min(32, remaining);
+    // candidate before the first edge of this batch (the state may already be armed)
+    int first_edge = nvalid;
+    int p_k = 1 << 20;
+    bool is_rise = false;
+    if (lane < nb) {
+      p_k = kth_set_bit128(E, done + lane);
+      is_rise = (RS[p_k >> 5] >> (p_k & 31)) & 1u;
+    }
+    if (nb > 0) first_edge = __shfl_sync(0xffffffffu, p_k, 0);
+    if (st.sig_pos && st.num_pulses > kNumPulsesCommand) {
+      const int p_open = pos + max(0, n_T1 - st.n_samples);
+      if (p_open < first_edge && p_open < nvalid) {  // a falling edge at the same position wins
+        st.sig_pos = true; st.num_pulses = 0; st.n_samples = 1;
+        return p_open;
+      }
+    }
+    if (nb == 0) { st.n_samples += nvalid - pos; return -1; }
+    // ---- one edge per lane
+    const int p_virtual = pos - 1 - st.n_samples;  // where the previous edge would sit
+    int p_prev = __shfl_up_sync(0xffffffffu, p_k, 1);
+    if (lane == 0) p_prev = p_virtual;
+    const bool valid_rise = (lane < nb) && is_rise && (p_k - p_prev > half_pw);   // n_samples > n_samples_PW/2
+    const bool bad_rise = (lane < nb) && is_rise && !(p_k - p_prev > half_pw);
+    const unsigned VR = __ballot_sync(0xffffffffu, valid_rise), IR = __ballot_sync(0xffffffffu, bad_rise);
+    // num_pulses after edge k: valid rises since the last invalid one (inclusive range), plus the carried
+    // count if no reset happened yet
+    const unsigned upto = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
+    const unsigned resets = IR & upto;
+    int np;
+    if (resets) {
+      const int last = 31 - __clz(resets);
+      np = __popc(VR & upto & ~((2u << last) - 1u));
+    } else {
+      np = st.num_pulses + __popc(VR & upto);
+    }
+    // next edge after lane k (next lane, or the first edge of the next batch, or none)
+    int p_next = __shfl_down_sync(0xffffffffu, p_k, 1);
+    if (lane == nb - 1) p_next = (remaining > nb) ? kth_set_bit128(E, done + nb) : nvalid;
+    const int p_open_k = p_k + 1 + n_T1;
+    const bool opens = (lane < nb) && is_rise && np > kNumPulsesCommand && p_open_k < p_next && p_open_k < nvalid;
+    const unsigned OM = __ballot_sync(0xffffffffu, opens);
+    if (OM) {
+      const int k = __ffs(OM) - 1;
+      const int p_open = __shfl_sync(0xffffffffu, p_open_k, k);
+      st.sig_pos = true; st.num_pulses = 0; st.n_samples = 1;
+      return p_open;
+    }
+    // ---- no opening in this batch: state after its last edge
+    const int kl = nb - 1;
+    const int p_last = __shfl_sync(0xffffffffu, p_k, kl);
+    st.sig_pos = __shfl_sync(0xffffffffu, (int)is_rise, kl) != 0;
+    st.num_pulses = __shfl_sync(0xffffffffu, np, kl);
+    st.n_samples = 0;
+    pos = p_last + 1;
+    done += nb;
+    remaining -= nb;
+  }
+}
+
+template <int DECIM, int MFQ>
+__global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const FusedArgs A)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ SplitShared B;
+
+  const int seg = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+#ifdef RFID_B200_PHASE_PROFILE
+  const long long ph_begin = clock64();
+#define PH_END(slot) if (lane == 0 && A.window_tap) reinterpret_cast<long long*>(A.window_tap)[(size_t)blockIdx.x * 24 + (slot)] = clock64() - ph_begin;
+#else
+#define PH_END(slot)
+#endif
+  // roles rotate over the hardware warps so that the chain warps of co-resident CTAs spread over the SM
+  // sub-partitions: 0 chain, 1 control, 2..3 workers, 4 decoder
+  const int role = ((threadIdx.x >> 5) + blockIdx.x) % 5;
+  const RxConfig& C = A.cfg;
+  const rfid_b200_segment sg = A.segs[seg];
+  const int n_out = (int)(sg.length / DECIM);
+  const int ntiles = (n_out + kTT - 1) / kTT;
+
+  float2* raw = reinterpret_cast<float2*>(smem + A.off_raw);
+  float2* bhist = reinterpret_cast<float2*>(smem + A.off_bhist);
+  float2* phist = bhist + A.bhist_size;
+  float2* ring_y = reinterpret_cast<float2*>(smem + A.off_tile_y);   // [kRing]
+  float* ring_a = reinterpret_cast<float*>(smem + A.off_tile_a);     // [kRing]
+  float* ring_d = reinterpret_cast<float*>(smem + A.off_tile_d);     // [kRing] (+pad): delta-amp, then avg_ampl in place
+  float* etile = reinterpret_cast<float*>(smem + A.off_etile);       // [kS][2][kTT] (+pad): DC-ring differences, then dc_est
+  float2* snap = reinterpret_cast<float2*>(smem + A.off_snap);
+  float2* dstage = reinterpret_cast<float2*>(smem + A.off_dstage);  // decoder's staging buffer
+  float2* const win_base = A.win_scratch + (size_t)seg * A.win_stride;
+
+  for (int i = threadIdx.x; i < A.bhist_size * (C.mf_rem ? 2 : 1); i += kSplitThreads) bhist[i] = make_float2(0.f, 0.f);
+  for (int i = threadIdx.x; i < kRing; i += kSplitThreads) { ring_y[i] = make_float2(0.f, 0.f); ring_a[i] = 0.f; }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRawStages; s++) mbar_init(&B.raw_full[s], 1);
+    for (int s = 0; s < kS; s++) {
+      mbar_init(&B.tile_full[s], kWorkerWarps);
+      mbar_init(&B.chain_done[s], 1);
+      mbar_init(&B.elist_ready[s], 1);
+      mbar_init(&B.tile_free[s], 1);
+      B.n_e[s] = 0;
+      B.n_ev[s] = 0;
+    }
+    for (int s = 0; s < 2; s++) { mbar_init(&B.win_ready[s], 1); mbar_init(&B.win_free[s], 1); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (role == 2 || role == 3) {
+    // =========================================================== workers
+    const int wt = (role - 2) * 32 + lane;
+    if (wt == 0) {
+      for (int k = 0; k < kRawStages && k < ntiles; k++)
+        issue_tile_load<DECIM>(A, sg, k, raw + (size_t)k * A.raw_stage_samples, &B.raw_full[k]);
+    }
+    const int bmask = A.bhist_size - 1;
+    const float winlen_f = (float)C.win_length, dclen_f = (float)C.dc_length;
+    PH_DECL
+    for (int k = 0; k < ntiles; k++) {
+      const int rs = k % kRawStages, ts = k % kS;
+      const float2* stage = raw + (size_t)rs * A.raw_stage_samples;
+      const int delta = (int)(tile_load_start<DECIM>(sg.offset, k) - (long long)DECIM * k * kTT);
+      const int nvalid = min(kTT, n_out - k * kTT);
+      PH_MARK(0)
+      mbar_wait(&B.raw_full[rs], (k / kRawStages) & 1);
+      PH_MARK(1)
+      // ---- block sums B(n) = x[D*n-D+1 .. D*n], ascending
+#pragma unroll
+      for (int r = 0; r < kTT / kWorkerThreads; r++) {
+        const int t = wt + r * kWorkerThreads;
+        if (t < nvalid) {
+          const int n = k * kTT + t;
+          const int base = DECIM * t - (DECIM - 1) - delta;
+          float2 x[DECIM];
+#pragma unroll
+          for (int j = 0; j < DECIM; j++) {
+            const bool before = (k == 0) && (DECIM * t - (DECIM - 1) + j < 0);  // before sample 0: +0
+            x[j] = before ? make_float2(0.f, 0.f) : stage[base + j];
+          }
+          float2 b = x[0];
+#pragma unroll
+          for (int j = 1; j < DECIM; j++) b = c_add(b, x[j]);
+          bhist[n & bmask] = b;
+          if (MFQ == 0 && C.mf_rem) {
+            float2 p = make_float2(0.f, 0.f);
+            bool started = false;
+#pragma unroll
+            for (int j = 0; j < DECIM; j++) {
+              if (j >= DECIM - C.mf_rem) {
+                p = started ? c_add(p, x[j]) : x[j];
+                started = true;
+              }
+            }
+            phist[n & bmask] = p;
+          }
+        }
+      }
+      PH_MARK(2)
+      bar_sync_workers();  // raw stage consumed, block sums visible
+      if (wt == 0 && k + kRawStages < ntiles)
+        issue_tile_load<DECIM>(A, sg, k + kRawStages, raw + (size_t)rs * A.raw_stage_samples, &B.raw_full[rs]);
+      PH_MARK(3)
+      mbar_wait_lazy(&B.tile_free[ts], ((k / kS) & 1) ^ 1);  // control is done with tile k - 5
+      PH_MARK(4)
+      float a_reg[kTT / kWorkerThreads];
+      float2 y_reg[kTT / kWorkerThreads];
+#pragma unroll
+      for (int r = 0; r < kTT / kWorkerThreads; r++) {
+        const int t = wt + r * kWorkerThreads;
+        a_reg[r] = 0.f;
+        y_reg[r] = make_float2(0.f, 0.f);
+        if (t < nvalid) {
+          const int n = k * kTT + t;
+          float2 y;
+          if (MFQ > 0) {
+            y = bhist[(n - MFQ + 1) & bmask];
+#pragma unroll
+            for (int m = MFQ - 2; m >= 0; m--) y = c_add(y, bhist[(n - m) & bmask]);
+          } else {
+            int m = n - C.mf_q + 1;
+            if (C.mf_rem) {
+              y = phist[(n - C.mf_q) & bmask];
+            } else {
+              y = bhist[m & bmask];
+              m++;
+            }
+            for (; m <= n; m++) y = c_add(y, bhist[m & bmask]);
+          }
+          const float a = cabsf_ref(y.x, y.y);  // gate_impl.cc:130
+          ring_y[ts * kTT + t] = y;
+          ring_a[ts * kTT + t] = a;
+          a_reg[r] = a;
+          y_reg[r] = y;
+        }
+      }
+      PH_MARK(5)
+      bar_sync_workers();  // this tile's |y| and y visible to both workers
+      PH_MARK(6)
+#pragma unroll
+      for (int r = 0; r < kTT / kWorkerThreads; r++) {
+        const int t = wt + r * kWorkerThreads;
+        if (t < nvalid) {
+          int ia = ts * kTT + t - C.win_length;
+          if (ia < 0) ia += kRing;
+          ring_d[ts * kTT + t] = f_div(f_sub(a_reg[r], ring_a[ia]), winlen_f);  // gate_impl.cc:131
+          int iy = ts * kTT + t - C.dc_length;
+          if (iy < 0) iy += kRing;
+          const float2 old = ring_y[iy];
+          etile[(ts * 2 + 0) * kTT + t] = f_div(f_sub(y_reg[r].x, old.x), dclen_f);  // gate_impl.cc:141, if time-contiguous
+          etile[(ts * 2 + 1) * kTT + t] = f_div(f_sub(y_reg[r].y, old.y), dclen_f);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B.tile_full[ts]);
+      PH_MARK(7)
+    }
+    if (wt == 0) { PH_DUMP(8) }
+    if (wt == 0) { PH_END(21) }
+  } else if (role == 0) {
+    // =========================================================== chain: the exact running sums, nothing else
+    float acc = 0.f;  // lane 0: avg_ampl, lane 1: dc_est.re, lane 2: dc_est.im
+    PH_DECL
+    for (int i = 0; i < ntiles + 2; i++) {
+      const int s = i % kS;
+      int n = 0;
+      PH_MARK(0)
+      float* buf = ring_d + s * kTT;
+      if (i < ntiles) {
+        mbar_wait(&B.tile_full[s], (i / kS) & 1);
+        if (lane == 0) n = min(kTT, n_out - i * kTT);
+      }
+      PH_MARK(1)
+      if (i >= 2) {
+        const int j = i - 2, sj = j % kS;
+        mbar_wait_hot(&B.elist_ready[sj], (j / kS) & 1);
+        if (lane == 1 || lane == 2) {
+          n = B.n_e[sj];
+          buf = etile + (sj * 2 + (lane - 1)) * kTT;
+        }
+      }
+      PH_MARK(2)
+      if (lane < 3) chain_inplace(buf, n, acc);
+      __syncwarp();
+      PH_MARK(3)
+      if (lane == 0) mbar_arrive(&B.chain_done[s]);
+    }
+    PH_DUMP(16)
+    PH_END(20)
+  } else if (role == 1) {
+    // =========================================================== control
+    bool sig_pos = false;          // signal_state, starts NEG_EDGE (gate_impl.cc:45)
+    int n_samples = 0, num_pulses = 0;
+    bool gate_open = false;
+    int to_ungate = C.len_rn16;    // first SEEK is for an RN16 (global_vars.cc:47, reader_impl.cc:262)
+    int wcount = 0, open_idx = 0;
+    bool cur_store = false;
+    int nq = 1;                    // n_queries_sent after START -> SEND_QUERY (reader_impl.cc:259)
+    bool terminated = false;
+    int closed_since = C.dc_length;
+    // emission state (two tiles behind)
+    bool f_open = false, f_store = false;
+    int f_wpos = 0, n_signalled = 0, n_freed = 0;
+    float2 dc_open = make_float2(0.f, 0.f);
+    float2* win = win_base;
+    const float dclen_f = (float)C.dc_length;
+    const int half_pw = C.n_PW / 2;
+    PH_DECL
+
+    for (int i = 0; i < ntiles + 2; i++) {
+      const int s = i % kS;
+      PH_MARK(0)
+      mbar_wait_hot(&B.chain_done[s], (i / kS) & 1);  // avg_ampl of tile i and dc_est of tile i-2 are final
+      PH_MARK(1)
+      // ---- thresholds + state machine of tile i; make its closed-sample list final
+      int nev = 0, n_e = 0;
+      if (i < ntiles) {
+        const int nvalid = min(kTT, n_out - i * kTT);
+        const float* davg = ring_d + s * kTT;
+        const float* ta = ring_a + s * kTT;
+        const float2* ty = ring_y + s * kTT;
+        float* er = etile + (s * 2 + 0) * kTT;
+        float* ei = er + kTT;
+        if (!terminated) {
+          unsigned lt[4], gt[4];
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            const int p = r * 32 + lane;
+            const bool v = p < nvalid;
+            const float thr = v ? f_mul(davg[p], kThreshFraction) : 0.f;  // gate_impl.cc:136
+            const float a = v ? ta[p] : 0.f;
+            lt[r] = __ballot_sync(0xffffffffu, v && a < thr);
+            gt[r] = __ballot_sync(0xffffffffu, v && a > thr);
+          }
+          PH_MARK(2)
+          int pos = 0;
+          while (pos < nvalid) {
+            if (!gate_open) {
+              // ---- closed: edges, pulse counting and the open test of this run in one warp-parallel step
+              const int run_start = pos;
+              GateFsm fs = {sig_pos, n_samples, num_pulses};
+              const int p_open = fsm_closed_run(lt, gt, run_start, nvalid, C.n_T1, half_pw, fs);
+              sig_pos = fs.sig_pos; n_samples = fs.n_samples; num_pulses = fs.num_pulses;
+              const bool opened = p_open >= 0;
+              pos = opened ? p_open + 1 : nvalid;
+              // ---- DC tracker inputs of the closed run [run_start, pos) (gate_impl.cc:141-143; includes the trigger)
+              const int len = pos - run_start;
+              if (run_start == 0 && pos == nvalid && !opened && closed_since >= C.dc_length) {
+                // no gate activity and the ring lookback is time-contiguous: the workers' differences are exact
+              } else {
+                for (int j = lane; j < len; j += 32) {
+                  const int p = run_start + j, m = closed_since + j;
+                  const float2 yv = ty[p];
+                  float2 old;
+                  if (m < C.dc_length) {
+                    old = snap[m];  // ring contents from before the window
+                  } else {
+                    int iy = s * kTT + p - C.dc_length;
+                    if (iy < 0) iy += kRing;
+                    old = ring_y[iy];
+                  }
+                  er[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
+                  ei[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
+                }
+              }
+              closed_since = min(closed_since + len, 1 << 24);
+              n_e += len;
+              if (opened) {
+                // READER COMMAND DETECTED (gate_impl.cc:164-180): keep the dc ring as it stands now
+                for (int j = lane; j < C.dc_length; j += 32) {
+                  int iy = s * kTT + (pos - 1) - C.dc_length + 1 + j;
+                  if (iy < 0) iy += kRing;
+                  snap[j] = ring_y[iy];
+                }
+                gate_open = true;
+                open_idx = i * kTT + pos - 1;
+                cur_store = wcount < A.max_windows;
+                if (lane == 0 && nev < kMaxTileEvents) {
+                  TileEvent& ev = B.ev[s][nev];
+                  ev.type = 1; ev.pos = pos - 1; ev.a = n_e - 1; ev.b = open_idx; ev.c = cur_store ? 1 : 0; ev.d = wcount & 1;
+                }
+                nev++;
+              }
+            } else {
+              // ---- open: samples pass through (gate_impl.cc:182-195); emitted two tiles later
+              const int take = min(to_ungate - n_samples, nvalid - pos);
+              n_samples += take; pos += take;
+              if (n_samples >= to_ungate) {
+                gate_open = false;
+                const int kind = wcount & 1;  // windows alternate RN16, EPC
+                if (lane == 0 && nev < kMaxTileEvents) {
+                  TileEvent& ev = B.ev[s][nev];
+                  ev.type = 2; ev.pos = pos; ev.a = kind; ev.b = wcount; ev.c = to_ungate; ev.d = open_idx;
+                }
+                nev++;
+                wcount++;
+                closed_since = 0;
+                // ACK after RN16 -> GATE_SEEK_EPC, Query/QueryRep after EPC -> GATE_SEEK_RN16 (gate_impl.cc:112-123)
+                to_ungate = kind ? C.len_rn16 : C.len_epc;
+                n_samples = 0;
+                if (kind) {
+                  nq++;
+                  if (nq > C.max_queries) { terminated = true; break; }  // gate_impl.cc:101-109
+                }
+              }
+            }
+          }
+        }
+        if (lane == 0) { B.n_e[s] = n_e; B.n_ev[s] = min(nev, kMaxTileEvents); }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B.elist_ready[s]);  // chain may run dc_est over this tile (iteration i+2)
+      }
+      PH_MARK(3)
+      // ---- finish tile i-2: window emission (gate_impl.cc:173,187) and hand-off to the decoder
+      if (i >= 2) {
+        const int t = i - 2, ps = t % kS;
+        const float2* py = ring_y + ps * kTT;
+        const float* pe_re = etile + (ps * 2 + 0) * kTT;
+        const float* pe_im = pe_re + kTT;
+        const int pvalid = min(kTT, n_out - t * kTT);
+        const int pnev = B.n_ev[ps];
+        int pos = 0;
+        for (int e = 0; e <= pnev; e++) {
+          const bool last = e == pnev;
+          const int etype = last ? 0 : B.ev[ps][e].type;
+          const int epos = last ? pvalid : B.ev[ps][e].pos;
+          if (f_open) {
+            const int take = epos - pos;
+            if (f_store)
+              for (int j = lane; j < take; j += 32) win[f_wpos + j] = c_sub(py[pos + j], dc_open);
+            f_wpos += take;
+            pos = epos;
+          }
+          if (etype == 2) {
+            f_open = false;
+            if (f_store) {
+              __syncwarp();
+              if (lane == 0) {
+                const int ms = n_signalled & 1;
+                B.meta_kind[ms] = B.ev[ps][e].a; B.meta_ordinal[ms] = B.ev[ps][e].b; B.meta_len[ms] = B.ev[ps][e].c; B.meta_open[ms] = B.ev[ps][e].d;
+              }
+              __threadfence();  // window samples were written to global memory
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&B.win_ready[n_signalled & 1]);
+              n_signalled++;
+            }
+            pos = epos;
+          } else if (etype == 1) {
+            const int j = B.ev[ps][e].a;
+            dc_open = make_float2(pe_re[j], pe_im[j]);  // dc_est right after the trigger sample
+            f_store = B.ev[ps][e].c != 0;
+            f_open = true;
+            win = win_base + (B.ev[ps][e].d ? A.rn16_pad : 0);
+            if (f_store) {
+              while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
+              if (lane == 0) win[0] = c_sub(py[epos], dc_open);
+            }
+            f_wpos = 1;
+            pos = epos + 1;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B.tile_free[ps]);  // workers may refill the stage of tile i-2
+      }
+      PH_MARK(4)
+    }
+    PH_DUMP(0)
+    while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
+    if (lane == 0) {
+      B.meta_kind[n_signalled & 1] = -1;
+      A.counts[seg] = wcount;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&B.win_ready[n_signalled & 1]);
+    PH_END(22)
+  } else {
+    // =========================================================== decoder
+    for (int j = 0;; j++) {
+      while (!mbar_try_wait(&B.win_ready[j & 1], (j >> 1) & 1)) __nanosleep(400);
+      const int kind = B.meta_kind[j & 1];
+      if (kind < 0) break;
+      const int ordinal = B.meta_ordinal[j & 1], open_idx = B.meta_open[j & 1], len = B.meta_len[j & 1];
+      const float2* win = win_base + (kind ? A.rn16_pad : 0);
+      WindowDecode wd;
+      decode_window_staged(C, kind, win, len, dstage, A.dstage_samples, wd);
+      rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
+      if (lane == 0) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
+#ifndef RFID_B200_PHASE_PROFILE
+      if (A.window_tap) {
+        float2* tap = A.window_tap + ((size_t)seg * A.max_windows + ordinal) * C.len_epc;
+        for (int p = lane; p < len; p += 32) tap[p] = __ldcg(win + p);
+      }
+#endif
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B.win_free[j & 1]);
+    }
+    PH_END(23)
+  }
+}
+
+}  // namespace rfid_b200

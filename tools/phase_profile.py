@@ -24,14 +24,15 @@ torch.cuda.synchronize()
 rx.set_window_tap(tap)
 rx.decode_capture(cap["iq"], segs, 2)
 torch.cuda.synchronize()
-t = tap.view(torch.int64).cpu().numpy().reshape(-1)[: nseg * 16].reshape(nseg, 16)
-seqn = ["tail", "wait_full", "chain", "finalize", "flags", "fsm+e"]
-wrk = ["loop", "wait_tma", "blocksum", "bar1", "wait_empty", "y+abs", "bar2", "d+arrive"]
-print("sequencer phases (mean cycles per segment over CTAs):")
-for i, nme in enumerate(seqn):
-    print("  %-10s %9.0f  per tile %7.0f" % (nme, t[:, i].mean(), t[:, i].mean() / 27))
-print("  total      %9.0f" % t[:, :6].sum(axis=1).mean())
-print("worker phases:")
-for i, nme in enumerate(wrk):
-    print("  %-10s %9.0f  per tile %7.0f" % (nme, t[:, 8 + i].mean(), t[:, 8 + i].mean() / 27))
-print("  total      %9.0f" % t[:, 8:16].sum(axis=1).mean())
+t = tap.view(torch.int64).cpu().numpy().reshape(-1)[: nseg * 24].reshape(nseg, 24)
+names = {0: ["ctl:loop", "ctl:wait_chain", "ctl:flags", "ctl:fsm+e", "ctl:emit"],
+         8: ["wrk:loop", "wrk:wait_tma", "wrk:blocksum", "wrk:bar1", "wrk:wait_free", "wrk:y+abs", "wrk:bar2", "wrk:d,e"],
+         16: ["chn:loop", "chn:wait_full", "chn:wait_elist", "chn:chain"]}
+for base, nm in names.items():
+    tot = 0
+    for i, x in enumerate(nm):
+        v = t[:, base + i].mean()
+        tot += v
+        print("  %-16s %9.0f  per tile %7.0f" % (x, v, v / 27))
+    print("  %-16s %9.0f" % ("= total", tot))
+print("role end times (cycles since CTA start): chain %.0f worker %.0f control %.0f decoder %.0f" % tuple(t[:, 20 + i].mean() for i in range(4)))
