@@ -45,50 +45,63 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock / throttle reasons sampled through NVML from a background thread (every ~0.5 ms) so that even a
+    millisecond-long timed region gets samples; `window(t0, t1)` summarises the samples taken inside it."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop_flag, self.th, self.ok = index, [], False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
+        if not self.ok:
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.0004)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-            except Exception:
-                continue
-            for k, nm in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=1)
+
+    def window(self, t0, t1):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        pad = 0.0
+        while len(inside) < 3 and pad < 0.2:   # very short region: widen symmetrically, say so
+            pad += 0.005
+            inside = [r for r in self.rows if t0 - pad <= r[0] <= t1 + pad]
+        reasons = set()
+        for r in inside:
+            for bit, nm in self.REASONS.items():
+                if r[2] & bit:
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(reasons), "samples": len(inside), "window_pad_ms": round(pad * 1e3, 1)}
 
 
 # ----------------------------------------------------------------------------------------- reference arm
@@ -246,16 +259,21 @@ def main():
     rx.kernel_time(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     ev0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
         launches += rx.last_launch_count()
     ev1.record(stream)
     barrier()
+    t_host1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     k_ms, k_n = rx.kernel_time(reset=True)
     rx.enable_kernel_timing(False)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.window(t_host0, t_host1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,9 +312,18 @@ def main():
         peak, peak_kind = hbm_peak()
         k_avg_ms = k_ms / max(1, k_n)
         achieved = 8.0 * n_raw / (k_avg_ms * 1e-3) / 1e9 if k_n else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if tj.get("rounds") == args.rounds:
+                    traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            except Exception:
+                pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None,
-                    "kernel": "rx_fused_kernel<5> (matched filter + gate + tag_decoder)",
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                    "kernel": "rx_fused_split_kernel<5,5> (matched filter + gate + tag_decoder, one CTA per segment)",
                     "kernel_ms": k_avg_ms, "kernel_launches_timed": k_n, "peak_kind": peak_kind,
                     "algorithmic_bytes_per_launch": 8.0 * n_raw}
         cpu_b = None

@@ -99,6 +99,16 @@ int derive_config(const rfid_b200_params& p, RxConfig& c)
   const float n = c.n_tag_bit_f;
   c.t_min = (float)(n / 2.0 - n / 2.0 / 100);  // :151
   c.t_max = (float)(n / 2.0 + n / 2.0 / 100);  // :152
+  // divisors for which RN(x/d) == fma(fma(-RN(x*c), d, x), c, RN(x*c)) holds for every binary32 x (exhaustive
+  // check: tools/micro/verify_constdiv.c, run by tests/test_host_logic.py)
+  static const int kVerifiedDivisors[] = {6, 24, 48, 50, 60, 96, 100, 125, 144, 192, 200, 300, 400};
+  c.win_recip = 1.0f / (float)c.win_length;
+  c.dc_recip = 1.0f / (float)c.dc_length;
+  c.win_div_fast = c.dc_div_fast = 0;
+  for (int d : kVerifiedDivisors) {
+    if (d == c.win_length) c.win_div_fast = 1;
+    if (d == c.dc_length) c.dc_div_fast = 1;
+  }
   if (c.win_length < 1 || c.dc_length < 1 || c.n_tag_bit_i < 1 || c.win_length > kMaxWinLen || c.dc_length > kMaxDcLen)
     return RFID_B200_EINVAL;
   return RFID_B200_OK;

@@ -48,6 +48,10 @@ struct RxConfig {
   int mf_q, mf_rem;        // ntaps / decim, ntaps % decim
   int sync_range;          // number of i with i < 1.5 * n_tag_bit_f   (tag_decoder_impl.cc:85)
   float t_min, t_max;      // EPC period search bounds (tag_decoder_impl.cc:151-152)
+  // division by the two ring lengths: reciprocal + "fast" flag when the multiply-correct sequence of
+  // f_div_const has been verified exhaustively for this divisor (tools/micro/verify_constdiv.c)
+  float win_recip, dc_recip;
+  int win_div_fast, dc_div_fast;
 };
 
 // ---------------------------------------------------------------- arithmetic primitives
@@ -55,6 +59,22 @@ __device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b
 __device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// IEEE-exact x / d for a constant d whose reciprocal c = RN(1/d) passed the exhaustive check: q = RN(x*c),
+// r = x - q*d (exact, fused), result = RN(q + r*c).  Three instructions instead of the ~10 of div.rn.  Only
+// applied where no intermediate can underflow / overflow; everything else takes the general division.
+__device__ __noinline__ float f_div_general(float x, float d) { return __fdiv_rn(x, d); }
+
+__device__ __forceinline__ float f_div_const(float x, float d, float c, int fast)
+{
+  const float ax = fabsf(x);
+  if (fast && ax >= 7.9e-31f && ax <= 1.2e30f) {
+    const float q = __fmul_rn(x, c);
+    const float r = __fmaf_rn(-q, d, x);
+    return __fmaf_rn(r, c, q);
+  }
+  return f_div_general(x, d);  // rare: out of the verified range, or an unverified divisor
+}
 
 // glibc cabsf(re + i*im): products are exact in double, one rounding for the sum, correctly
 // rounded double sqrt, one rounding to float.

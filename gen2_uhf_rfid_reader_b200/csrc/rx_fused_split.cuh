@@ -36,17 +36,35 @@ struct SplitShared {
   TileEvent ev[kS][kMaxTileEvents];
 };
 
+// Named (hardware) barriers for the hand-offs that are waited on all the time -- a warp parked at bar.sync costs no
+// issue slots: chain -> control ("chain_done"), control -> chain ("elist_ready"), control -> decoder ("win_ready").
+// Two ids each, alternating: at most two arrivals can be outstanding on any of them (see the comments at the
+// arrive sites).  Ids are immediates so ptxas reserves 8 barriers per CTA, not 16.
+enum : int { SBAR_WIN_READY = 2, SBAR_CHAIN_DONE = 4, SBAR_ELIST = 6 };
+template <int BASE>
+__device__ __forceinline__ void bar2_sync(int parity)
+{
+  if (parity == 0) asm volatile("bar.sync %0, 64;" ::"n"((int)BASE) : "memory");
+  else asm volatile("bar.sync %0, 64;" ::"n"((int)(BASE + 1)) : "memory");
+}
+template <int BASE>
+__device__ __forceinline__ void bar2_arrive(int parity)
+{
+  __threadfence_block();
+  if (parity == 0) asm volatile("bar.arrive %0, 64;" ::"n"((int)BASE) : "memory");
+  else asm volatile("bar.arrive %0, 64;" ::"n"((int)(BASE + 1)) : "memory");
+}
+
 // a wait that is off the critical path: poll rarely
 __device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity)
 {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(250);
+  while (!mbar_try_wait(bar, parity)) __nanosleep(1000);
 }
 // a wait on the critical path: poll back to back
 __device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity)
 {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  mbar_wait_relaxed(bar, parity, 2000);  // try_wait with a suspend hint: the hardware parks the warp until the phase flips
 }
 
 // ---- the edge/pulse state machine of one closed run, warp-parallel -------------------------------------
@@ -63,20 +81,22 @@ struct GateFsm {
   int n_samples, num_pulses;
 };
 
-__device__ __forceinline__ int kth_set_bit128(const unsigned w[4], int k)
+__device__ __forceinline__ int kth_set_bit128(unsigned w0, unsigned w1, unsigned w2, unsigned w3, int k)
 {
-  const int c0 = __popc(w[0]), c1 = c0 + __popc(w[1]), c2 = c1 + __popc(w[2]);
+  const int c0 = __popc(w0), c1 = c0 + __popc(w1), c2 = c1 + __popc(w2);
   int word = 0, r = k;
-  unsigned sel = w[0];
-  if (k >= c2) { word = 3; r = k - c2; sel = w[3]; }
-  else if (k >= c1) { word = 2; r = k - c1; sel = w[2]; }
-  else if (k >= c0) { word = 1; r = k - c0; sel = w[1]; }
+  unsigned sel = w0;
+  if (k >= c2) { word = 3; r = k - c2; sel = w3; }
+  else if (k >= c1) { word = 2; r = k - c1; sel = w2; }
+  else if (k >= c0) { word = 1; r = k - c0; sel = w1; }
   return 32 * word + (int)__fns(sel, 0, r + 1);
 }
 
 // Processes the closed samples [from, nvalid) of a tile.  Returns the position at which the gate opens
 // (the trigger sample, state updated for the open gate) or -1 (state advanced to the end of the tile).
-__device__ __forceinline__ int fsm_closed_run(const unsigned lt[4], const unsigned gt[4], int from, int nvalid, int n_T1,
+struct Mask128 { unsigned w[4]; };
+
+__device__ __forceinline__ int fsm_closed_run(const Mask128& lt, const Mask128& gt, int from, int nvalid, int n_T1,
                                               int half_pw, GateFsm& st)
 {
   const int lane = threadIdx.x & 31;
@@ -88,8 +108,8 @@ __device__ __forceinline__ int fsm_closed_run(const unsigned lt[4], const unsign
     // positions before `from` keep the state (they belong to an earlier run / an open window)
     const int lo = from - 32 * w;
     const unsigned live = lo <= 0 ? 0xffffffffu : (lo >= 32 ? 0u : (0xffffffffu << lo));
-    F[w] = lt[w] & live;
-    R[w] = gt[w] & live;
+    F[w] = lt.w[w] & live;
+    R[w] = gt.w[w] & live;
     const unsigned Pk = ~(F[w] | R[w]);
     const unsigned Aw = R[w] | Pk, Bw = R[w];
     const unsigned long long sum = (unsigned long long)Aw + Bw + carry;
@@ -112,8 +132,10 @@ __device__ __forceinline__ int fsm_closed_run(const unsigned lt[4], const unsign
     int p_k = 1 << 20;
     bool is_rise = false;
     if (lane < nb) {
-      p_k = kth_set_bit128(E, done + lane);
-      is_rise = (RS[p_k >> 5] >> (p_k & 31)) & 1u;
+      p_k = kth_set_bit128(E[0], E[1], E[2], E[3], done + lane);
+      const int wsel = p_k >> 5;
+      const unsigned rsw = wsel == 0 ? RS[0] : (wsel == 1 ? RS[1] : (wsel == 2 ? RS[2] : RS[3]));
+      is_rise = (rsw >> (p_k & 31)) & 1u;
     }
     if (nb > 0) first_edge = __shfl_sync(0xffffffffu, p_k, 0);
     if (st.sig_pos && st.num_pulses > kNumPulsesCommand) {
@@ -144,7 +166,7 @@ __device__ __forceinline__ int fsm_closed_run(const unsigned lt[4], const unsign
     }
     // next edge after lane k (next lane, or the first edge of the next batch, or none)
     int p_next = __shfl_down_sync(0xffffffffu, p_k, 1);
-    if (lane == nb - 1) p_next = (remaining > nb) ? kth_set_bit128(E, done + nb) : nvalid;
+    if (lane == nb - 1) p_next = (remaining > nb) ? kth_set_bit128(E[0], E[1], E[2], E[3], done + nb) : nvalid;
     const int p_open_k = p_k + 1 + n_T1;
     const bool opens = (lane < nb) && is_rise && np > kNumPulsesCommand && p_open_k < p_next && p_open_k < nvalid;
     const unsigned OM = __ballot_sync(0xffffffffu, opens);
@@ -310,14 +332,16 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       for (int r = 0; r < kTT / kWorkerThreads; r++) {
         const int t = wt + r * kWorkerThreads;
         if (t < nvalid) {
+          const float a_cur = a_reg[r];
+          const float2 y_cur = y_reg[r];
           int ia = ts * kTT + t - C.win_length;
           if (ia < 0) ia += kRing;
-          ring_d[ts * kTT + t] = f_div(f_sub(a_reg[r], ring_a[ia]), winlen_f);  // gate_impl.cc:131
+          ring_d[ts * kTT + t] = f_div_const(f_sub(a_cur, ring_a[ia]), winlen_f, C.win_recip, C.win_div_fast);  // gate_impl.cc:131
           int iy = ts * kTT + t - C.dc_length;
           if (iy < 0) iy += kRing;
           const float2 old = ring_y[iy];
-          etile[(ts * 2 + 0) * kTT + t] = f_div(f_sub(y_reg[r].x, old.x), dclen_f);  // gate_impl.cc:141, if time-contiguous
-          etile[(ts * 2 + 1) * kTT + t] = f_div(f_sub(y_reg[r].y, old.y), dclen_f);
+          etile[(ts * 2 + 0) * kTT + t] = f_div_const(f_sub(y_cur.x, old.x), dclen_f, C.dc_recip, C.dc_div_fast);  // gate_impl.cc:141, if time-contiguous
+          etile[(ts * 2 + 1) * kTT + t] = f_div_const(f_sub(y_cur.y, old.y), dclen_f, C.dc_recip, C.dc_div_fast);
         }
       }
       __syncwarp();
@@ -342,7 +366,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       PH_MARK(1)
       if (i >= 2) {
         const int j = i - 2, sj = j % kS;
-        mbar_wait_hot(&B.elist_ready[sj], (j / kS) & 1);
+        bar2_sync<SBAR_ELIST>(j & 1);  // control has fixed the closed-sample list of tile i-2
         if (lane == 1 || lane == 2) {
           n = B.n_e[sj];
           buf = etile + (sj * 2 + (lane - 1)) * kTT;
@@ -352,7 +376,9 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       if (lane < 3) chain_inplace(buf, n, acc);
       __syncwarp();
       PH_MARK(3)
-      if (lane == 0) mbar_arrive(&B.chain_done[s]);
+      // control syncs on chain_done(i) before it publishes elist_ready(i), which this warp needs for
+      // iteration i+2: never more than two arrivals outstanding => ids alternate with i
+      bar2_arrive<SBAR_CHAIN_DONE>(i & 1);
     }
     PH_DUMP(16)
     PH_END(20)
@@ -379,7 +405,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
     for (int i = 0; i < ntiles + 2; i++) {
       const int s = i % kS;
       PH_MARK(0)
-      mbar_wait_hot(&B.chain_done[s], (i / kS) & 1);  // avg_ampl of tile i and dc_est of tile i-2 are final
+      bar2_sync<SBAR_CHAIN_DONE>(i & 1);  // avg_ampl of tile i and dc_est of tile i-2 are final
       PH_MARK(1)
       // ---- thresholds + state machine of tile i; make its closed-sample list final
       int nev = 0, n_e = 0;
@@ -407,9 +433,20 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
             if (!gate_open) {
               // ---- closed: edges, pulse counting and the open test of this run in one warp-parallel step
               const int run_start = pos;
-              GateFsm fs = {sig_pos, n_samples, num_pulses};
-              const int p_open = fsm_closed_run(lt, gt, run_start, nvalid, C.n_T1, half_pw, fs);
-              sig_pos = fs.sig_pos; n_samples = fs.n_samples; num_pulses = fs.num_pulses;
+              int p_open = -1;
+              if (sig_pos && (lt[0] | lt[1] | lt[2] | lt[3]) == 0u) {
+                // carrier only (the common case): no falling edge can occur, only the open test remains
+                if (num_pulses > kNumPulsesCommand) {
+                  const int cand = run_start + max(0, C.n_T1 - n_samples);
+                  if (cand < nvalid) { p_open = cand; num_pulses = 0; n_samples = 1; }
+                }
+                if (p_open < 0) n_samples += nvalid - run_start;
+              } else {
+                GateFsm fs = {sig_pos, n_samples, num_pulses};
+                const Mask128 ltm = {{lt[0], lt[1], lt[2], lt[3]}}, gtm = {{gt[0], gt[1], gt[2], gt[3]}};
+                p_open = fsm_closed_run(ltm, gtm, run_start, nvalid, C.n_T1, half_pw, fs);
+                sig_pos = fs.sig_pos; n_samples = fs.n_samples; num_pulses = fs.num_pulses;
+              }
               const bool opened = p_open >= 0;
               pos = opened ? p_open + 1 : nvalid;
               // ---- DC tracker inputs of the closed run [run_start, pos) (gate_impl.cc:141-143; includes the trigger)
@@ -417,6 +454,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
               if (run_start == 0 && pos == nvalid && !opened && closed_since >= C.dc_length) {
                 // no gate activity and the ring lookback is time-contiguous: the workers' differences are exact
               } else {
+#pragma unroll 1
                 for (int j = lane; j < len; j += 32) {
                   const int p = run_start + j, m = closed_since + j;
                   const float2 yv = ty[p];
@@ -428,14 +466,15 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
                     if (iy < 0) iy += kRing;
                     old = ring_y[iy];
                   }
-                  er[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
-                  ei[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
+                  er[n_e + j] = f_div_const(f_sub(yv.x, old.x), dclen_f, C.dc_recip, C.dc_div_fast);
+                  ei[n_e + j] = f_div_const(f_sub(yv.y, old.y), dclen_f, C.dc_recip, C.dc_div_fast);
                 }
               }
               closed_since = min(closed_since + len, 1 << 24);
               n_e += len;
               if (opened) {
                 // READER COMMAND DETECTED (gate_impl.cc:164-180): keep the dc ring as it stands now
+#pragma unroll 1
                 for (int j = lane; j < C.dc_length; j += 32) {
                   int iy = s * kTT + (pos - 1) - C.dc_length + 1 + j;
                   if (iy < 0) iy += kRing;
@@ -477,7 +516,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         }
         if (lane == 0) { B.n_e[s] = n_e; B.n_ev[s] = min(nev, kMaxTileEvents); }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&B.elist_ready[s]);  // chain may run dc_est over this tile (iteration i+2)
+        bar2_arrive<SBAR_ELIST>(i & 1);  // chain may run dc_est over this tile (its iteration i+2)
       }
       PH_MARK(3)
       // ---- finish tile i-2: window emission (gate_impl.cc:173,187) and hand-off to the decoder
@@ -510,7 +549,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
               }
               __threadfence();  // window samples were written to global memory
               __syncwarp();
-              if (lane == 0) mbar_arrive(&B.win_ready[n_signalled & 1]);
+              bar2_arrive<SBAR_WIN_READY>(n_signalled & 1);  // hand-off n-2 was consumed before this window opened
               n_signalled++;
             }
             pos = epos;
@@ -539,14 +578,13 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       B.meta_kind[n_signalled & 1] = -1;
       A.counts[seg] = wcount;
     }
-    __threadfence_block();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&B.win_ready[n_signalled & 1]);
+    bar2_arrive<SBAR_WIN_READY>(n_signalled & 1);
     PH_END(22)
   } else {
     // =========================================================== decoder
     for (int j = 0;; j++) {
-      while (!mbar_try_wait(&B.win_ready[j & 1], (j >> 1) & 1)) __nanosleep(400);
+      bar2_sync<SBAR_WIN_READY>(j & 1);  // parked by the hardware until the control warp hands a window over
       const int kind = B.meta_kind[j & 1];
       if (kind < 0) break;
       const int ordinal = B.meta_ordinal[j & 1], open_idx = B.meta_open[j & 1], len = B.meta_len[j & 1];
