@@ -211,10 +211,19 @@ __host__ __device__ inline int decode_stage_samples(float n_tag_bit)
   return ((int)(32.5f * n_tag_bit * 1.0101f) + 16 + 7) & ~7;
 }
 
-__device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail)
+// `progress` (may be null): number of window samples the producer has published so far; the fill waits until
+// the range it is about to read exists.  This is what lets the decoder work on a window WHILE it is still being
+// gated (streaming decode), instead of starting when the window closes.
+__device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail,
+                                           const volatile int* progress = nullptr)
 {
   const int lane = threadIdx.x & 31;
   __syncwarp();
+  if (progress) {
+    const int need = min(n_avail, lo + count);
+    while (*progress < need) __nanosleep(300);
+    __threadfence_block();  // the samples were written (and fenced, CTA scope) before the counter moved
+  }
   for (int p = lane; p < count; p += 32) {
     const int g = lo + p;
     stage[p] = (g >= 0 && g < n_avail) ? __ldcg(gw + g) : make_float2(0.f, 0.f);
@@ -223,7 +232,8 @@ __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restri
 }
 
 __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
-                                                     float2* __restrict__ stage, int stage_cap, WindowDecode& out)
+                                                     float2* __restrict__ stage, int stage_cap, WindowDecode& out,
+                                                     const volatile int* progress = nullptr)
 {
   const int lane = threadIdx.x & 31;
   const float n = c.n_tag_bit_f;
@@ -231,7 +241,7 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
 
   // ---- tag_sync + h_est need w[0 .. sync_range + 5.5 n): one stage fill (an RN16 window fits entirely)
   const int head = min(stage_cap, kind == RFID_B200_RN16 ? n_avail : (int)(c.sync_range + 6.0f * n) + 2);
-  stage_fill(stage, gw, 0, head, n_avail);
+  stage_fill(stage, gw, 0, head, n_avail, progress);
   float best = -1.0f;
   int best_i = 0x7fffffff;
   for (int i = lane; i < c.sync_range; i += 32) {
@@ -312,7 +322,7 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
   float e = 0.0f;
   for (int i0 = 0; i0 < 256; i0 += 32) {
     const int lo = (int)f_add(f_mul((float)i0, min_val), (float)index);  // smallest index any candidate touches
-    stage_fill(stage, gw, lo, min(stage_cap, (int)(32.0f * max_val + 256.0f * (max_val - min_val)) + 8), n_avail);
+    stage_fill(stage, gw, lo, min(stage_cap, (int)(32.0f * max_val + 256.0f * (max_val - min_val)) + 8), n_avail, progress);
     if (lane < number_steps) {
 #pragma unroll 8
       for (int i = i0; i < i0 + 32; i++) {
@@ -334,7 +344,7 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
   for (int r = 0; r < 4; r++) {
     const int j0 = r * 32;
     const int lo = (int)f_add(f_mul((float)j0, twoT), (float)index);
-    stage_fill(stage, gw, lo, stage_cap, n_avail);
+    stage_fill(stage, gw, lo, stage_cap, n_avail, progress);
     int j = j0 + lane;
     int a = (int)f_add(f_mul((float)j, twoT), (float)index);
     int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);

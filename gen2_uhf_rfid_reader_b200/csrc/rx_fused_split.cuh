@@ -31,6 +31,8 @@ struct SplitShared {
   uint64_t tile_free[kS];    // control (1)           -> workers
   uint64_t win_ready[2], win_free[2];
   int meta_kind[2], meta_open[2], meta_ordinal[2], meta_len[2];
+  int progress[2];           // window samples published so far (streaming decode)
+  int aborted[2];            // the capture ended inside this window: finish the decode, store nothing
   int n_e[kS];               // closed samples in the DC list of each stage
   int n_ev[kS];
   TileEvent ev[kS][kMaxTileEvents];
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
     int closed_since = C.dc_length;
     // emission state (two tiles behind)
     bool f_open = false, f_store = false;
-    int f_wpos = 0, n_signalled = 0, n_freed = 0;
+    int f_wpos = 0, n_signalled = 0, n_freed = 0, f_slot = 0, wsig_ordinal = 0;
     float2 dc_open = make_float2(0.f, 0.f);
     float2* win = win_base;
     const float dclen_f = (float)C.dc_length;
@@ -534,24 +536,17 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
           const int epos = last ? pvalid : B.ev[ps][e].pos;
           if (f_open) {
             const int take = epos - pos;
-            if (f_store)
+            if (f_store && take > 0) {
               for (int j = lane; j < take; j += 32) win[f_wpos + j] = c_sub(py[pos + j], dc_open);
+              __threadfence_block();  // samples first, then the counter the decoder (same CTA) polls
+              __syncwarp();
+              if (lane == 0) *(volatile int*)&B.progress[f_slot] = f_wpos + take;
+            }
             f_wpos += take;
             pos = epos;
           }
           if (etype == 2) {
-            f_open = false;
-            if (f_store) {
-              __syncwarp();
-              if (lane == 0) {
-                const int ms = n_signalled & 1;
-                B.meta_kind[ms] = B.ev[ps][e].a; B.meta_ordinal[ms] = B.ev[ps][e].b; B.meta_len[ms] = B.ev[ps][e].c; B.meta_open[ms] = B.ev[ps][e].d;
-              }
-              __threadfence();  // window samples were written to global memory
-              __syncwarp();
-              bar2_arrive<SBAR_WIN_READY>(n_signalled & 1);  // hand-off n-2 was consumed before this window opened
-              n_signalled++;
-            }
+            f_open = false;  // the decoder already has the window: it saw progress reach its length
             pos = epos;
           } else if (etype == 1) {
             const int j = B.ev[ps][e].a;
@@ -560,9 +555,25 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
             f_open = true;
             win = win_base + (B.ev[ps][e].d ? A.rn16_pad : 0);
             if (f_store) {
+              // the scratch area and the meta slot are reused two hand-offs later
               while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
-              if (lane == 0) win[0] = c_sub(py[epos], dc_open);
+              f_slot = n_signalled & 1;
+              if (lane == 0) {
+                win[0] = c_sub(py[epos], dc_open);
+                const int knd = B.ev[ps][e].d;
+                B.meta_kind[f_slot] = knd; B.meta_ordinal[f_slot] = wsig_ordinal; B.meta_open[f_slot] = B.ev[ps][e].b;
+                B.meta_len[f_slot] = knd ? C.len_epc : C.len_rn16;
+                *(volatile int*)&B.progress[f_slot] = 0;
+                B.aborted[f_slot] = 0;
+              }
+              __threadfence_block();
+              __syncwarp();
+              if (lane == 0) *(volatile int*)&B.progress[f_slot] = 1;
+              // hand the window to the decoder NOW: it decodes while the gate is still open (streaming)
+              bar2_arrive<SBAR_WIN_READY>(f_slot);
+              n_signalled++;
             }
+            wsig_ordinal++;
             f_wpos = 1;
             pos = epos + 1;
           }
@@ -573,6 +584,13 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       PH_MARK(4)
     }
     PH_DUMP(0)
+    if (f_open && f_store && lane == 0) {
+      // the segment ended inside a window the decoder is already working on: let it run to the end
+      *(volatile int*)&B.aborted[f_slot] = 1;
+      __threadfence_block();
+      *(volatile int*)&B.progress[f_slot] = 1 << 30;
+    }
+    __syncwarp();
     while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
     if (lane == 0) {
       B.meta_kind[n_signalled & 1] = -1;
@@ -590,9 +608,10 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       const int ordinal = B.meta_ordinal[j & 1], open_idx = B.meta_open[j & 1], len = B.meta_len[j & 1];
       const float2* win = win_base + (kind ? A.rn16_pad : 0);
       WindowDecode wd;
-      decode_window_staged(C, kind, win, len, dstage, A.dstage_samples, wd);
+      decode_window_staged(C, kind, win, len, dstage, A.dstage_samples, wd, (const volatile int*)&B.progress[j & 1]);
       rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
-      if (lane == 0) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
+      const bool aborted = *(volatile int*)&B.aborted[j & 1] != 0;
+      if (lane == 0 && !aborted) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
 #ifndef RFID_B200_PHASE_PROFILE
       if (A.window_tap) {
         float2* tap = A.window_tap + ((size_t)seg * A.max_windows + ordinal) * C.len_epc;
