@@ -118,3 +118,20 @@ def test_reader_block_matches_reference_sample_for_sample(ref_flow):
     assert [c for k, c in cmds if k == "preamble"][0] == gold["queries"][0]
     acks = [c for k, c in cmds if k == "framesync" and len(c) == 18]
     assert acks[0] == "01" + "".join(str(int(x)) for x in bits[0])
+
+
+def test_constant_division_sequence_is_exact_for_every_float():
+    """the 3-instruction multiply-correct division used by the kernels equals IEEE x/d for EVERY binary32
+    mantissa, for every divisor the host marks as 'fast' (csrc/rfid_b200.cu kVerifiedDivisors + 6, 19)"""
+    import re
+    import subprocess
+    src = open(os.path.join(ROOT, "gen2_uhf_rfid_reader_b200", "csrc", "rfid_b200.cu")).read()
+    m = re.search(r"kVerifiedDivisors\[\] = \{([^}]*)\}", src)
+    divs = sorted(set(int(x) for x in m.group(1).split(",")) | {6, 19})
+    exe = "/tmp/verify_constdiv_%d" % os.getpid()
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe,
+                           os.path.join(ROOT, "tools", "micro", "verify_constdiv.c"), "-lm"])
+    out = subprocess.run([exe] + [str(d) for d in divs], capture_output=True, text=True)
+    os.unlink(exe)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count(": 0 mismatches") == len(divs)
