@@ -8,7 +8,7 @@ inventory-round segments of 16,960 raw samples), 1 tag, per GPU.  One *step* = o
 one such capture.  `value` is timed with the captures already resident in HBM; `e2e` goes through the
 host-pointer C-ABI call with pinned host buffers (H2D of the capture and D2H of the records inside the
 timed region).  Weak scaling: every rank decodes its own 1000-round shard of the global segment table; the
-one collective is an all-gather of the decoded records at the end of each step.
+one collective is a single all-gather of the decoded records of all K steps at the end of the timed region.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref: its blocks compiled unchanged)
 on all host cores over the same workload.
@@ -184,7 +184,7 @@ def main():
                           % (args.rounds, seg_len),
               "rounds_per_gpu": args.rounds, "segment_samples": seg_len, "fixed_q": 0,
               "l2": "inputs larger than L2: %d distinct captures of %.0f MB cycled" % (NBUF, args.rounds * seg_len * 8 / 1e6),
-              "parallelism": "segments sharded over %d GPU(s), all-gather of records per step" % world}
+              "parallelism": "segments sharded over %d GPU(s), one all-gather of all decoded records at the end of the timed region" % world}
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
@@ -224,18 +224,23 @@ def main():
             segs_np = cap["segments"]
             seg_dev = capi.segments_to_device(segs_np, dev)
     n_raw = caps[0].numel()
-    results = torch.zeros((args.rounds * MAX_WINDOWS, 64), dtype=torch.uint8, device=dev)
-    counts = torch.zeros(args.rounds, dtype=torch.int32, device=dev)
-    g_res = torch.empty((world * args.rounds * MAX_WINDOWS, 64), dtype=torch.uint8, device=dev)
-    g_cnt = torch.empty(world * args.rounds, dtype=torch.int32, device=dev)
+    # every step keeps its records on the device; ONE all-gather of all of them closes the timed region
+    # (north star: "a single NCCL gather of decoded EPCs at the end")
+    nslots = max(args.steps, args.warmup)
+    results_all = torch.zeros((nslots, args.rounds * MAX_WINDOWS, 64), dtype=torch.uint8, device=dev)
+    counts_all = torch.zeros((nslots, args.rounds), dtype=torch.int32, device=dev)
+    g_res = torch.empty((world,) + tuple(results_all.shape), dtype=torch.uint8, device=dev) if world > 1 else None
+    g_cnt = torch.empty((world,) + tuple(counts_all.shape), dtype=torch.int32, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream(dev)
     launches = 0
 
-    def step(i):
-        rx.decode_capture(caps[i % NBUF], seg_dev, MAX_WINDOWS, results, counts, stream)
+    def step(i, slot):
+        rx.decode_capture(caps[i % NBUF], seg_dev, MAX_WINDOWS, results_all[slot], counts_all[slot], stream)
+
+    def gather():
         if world > 1:
-            dist.all_gather_into_tensor(g_res, results)
-            dist.all_gather_into_tensor(g_cnt, counts)
+            dist.all_gather_into_tensor(g_res, results_all)
+            dist.all_gather_into_tensor(g_cnt, counts_all)
 
     def barrier():
         if world > 1:
@@ -243,10 +248,11 @@ def main():
         torch.cuda.synchronize(dev)
 
     for i in range(args.warmup):
-        step(i)
+        step(i, i)
+    gather()
     barrier()
     # correctness gate on the warm-up output: every round must decode its tag's EPC with a valid CRC
-    recs, cnt = capi.results_to_numpy(results, counts, MAX_WINDOWS)
+    recs, cnt = capi.results_to_numpy(results_all[args.warmup - 1], counts_all[args.warmup - 1], MAX_WINDOWS)
     epc_ok = int((recs[:, 1]["crc_ok"] == 1).sum())
     truth = truths[(args.warmup - 1) % NBUF]
     rn_ok = int((recs[:, 0]["tag_id"] == truth["rn16"]).sum())
@@ -262,8 +268,9 @@ def main():
     t_host0 = time.perf_counter()
     ev0.record(stream)
     for i in range(args.steps):
-        step(args.warmup + i)
+        step(args.warmup + i, i)
         launches += rx.last_launch_count()
+    gather()
     ev1.record(stream)
     barrier()
     t_host1 = time.perf_counter()

@@ -35,6 +35,7 @@ struct SplitShared {
   int aborted[2];            // the capture ended inside this window: finish the decode, store nothing
   int n_e[kS];               // closed samples in the DC list of each stage
   int n_ev[kS];
+  uint4 lt_mask[kS], gt_mask[kS];  // a < thr / a > thr per sample of the stage (computed by the chain warp)
   TileEvent ev[kS][kMaxTileEvents];
 };
 
@@ -61,7 +62,7 @@ __device__ __forceinline__ void bar2_arrive(int parity)
 __device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity)
 {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(1000);
+  while (!mbar_try_wait(bar, parity)) __nanosleep(2000);
 }
 // a wait on the critical path: poll back to back
 __device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity)
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
     }
     const int bmask = A.bhist_size - 1;
     const float winlen_f = (float)C.win_length, dclen_f = (float)C.dc_length;
+    float2 b_keep = make_float2(0.f, 0.f);
     PH_DECL
     for (int k = 0; k < ntiles; k++) {
       const int rs = k % kRawStages, ts = k % kS;
@@ -274,7 +276,12 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
           float2 b = x[0];
 #pragma unroll
           for (int j = 1; j < DECIM; j++) b = c_add(b, x[j]);
-          bhist[n & bmask] = b;
+          if (MFQ > 0) {
+            bhist[MFQ - 1 + t] = b;               // bhist[0 .. MFQ-2] = the last MFQ-1 block sums of the previous tile
+            if (t >= kTT - (MFQ - 1)) b_keep = b;  // ... which these threads hand over after the tile
+          } else {
+            bhist[n & bmask] = b;
+          }
           if (MFQ == 0 && C.mf_rem) {
             float2 p = make_float2(0.f, 0.f);
             bool started = false;
@@ -307,9 +314,10 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
           const int n = k * kTT + t;
           float2 y;
           if (MFQ > 0) {
-            y = bhist[(n - MFQ + 1) & bmask];
+            const float2* bp = bhist + t;  // B(n-MFQ+1) .. B(n) are bp[0 .. MFQ-1]
+            y = bp[0];
 #pragma unroll
-            for (int m = MFQ - 2; m >= 0; m--) y = c_add(y, bhist[(n - m) & bmask]);
+            for (int m = 1; m < MFQ; m++) y = c_add(y, bp[m]);
           } else {
             int m = n - C.mf_q + 1;
             if (C.mf_rem) {
@@ -328,8 +336,12 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         }
       }
       PH_MARK(5)
-      bar_sync_workers();  // this tile's |y| and y visible to both workers
+      bar_sync_workers();  // this tile's |y| and y visible to both workers; every block sum has been consumed
       PH_MARK(6)
+      if (MFQ > 0) {
+        const int t_hi = wt + kWorkerThreads * (kTT / kWorkerThreads - 1);  // this thread's last output of the tile
+        if (t_hi >= kTT - (MFQ - 1) && t_hi < nvalid) bhist[t_hi - (kTT - (MFQ - 1))] = b_keep;
+      }
 #pragma unroll
       for (int r = 0; r < kTT / kWorkerThreads; r++) {
         const int t = wt + r * kWorkerThreads;
@@ -377,6 +389,26 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       PH_MARK(2)
       if (lane < 3) chain_inplace(buf, n, acc);
       __syncwarp();
+      if (i < ntiles) {
+        // thresholds of tile i (gate_impl.cc:136,148,154) while the control warp is still busy with tile i-1
+        const int nv = min(kTT, n_out - i * kTT);
+        const float* davg = ring_d + s * kTT;
+        const float* ta = ring_a + s * kTT;
+        unsigned lt[4], gt[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int p = r * 32 + lane;
+          const bool v = p < nv;
+          const float thr = v ? f_mul(davg[p], kThreshFraction) : 0.f;
+          const float a = v ? ta[p] : 0.f;
+          lt[r] = __ballot_sync(0xffffffffu, v && a < thr);
+          gt[r] = __ballot_sync(0xffffffffu, v && a > thr);
+        }
+        if (lane == 0) {
+          B.lt_mask[s] = make_uint4(lt[0], lt[1], lt[2], lt[3]);
+          B.gt_mask[s] = make_uint4(gt[0], gt[1], gt[2], gt[3]);
+        }
+      }
       PH_MARK(3)
       // control syncs on chain_done(i) before it publishes elist_ready(i), which this warp needs for
       // iteration i+2: never more than two arrivals outstanding => ids alternate with i
@@ -419,16 +451,8 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         float* er = etile + (s * 2 + 0) * kTT;
         float* ei = er + kTT;
         if (!terminated) {
-          unsigned lt[4], gt[4];
-#pragma unroll
-          for (int r = 0; r < 4; r++) {
-            const int p = r * 32 + lane;
-            const bool v = p < nvalid;
-            const float thr = v ? f_mul(davg[p], kThreshFraction) : 0.f;  // gate_impl.cc:136
-            const float a = v ? ta[p] : 0.f;
-            lt[r] = __ballot_sync(0xffffffffu, v && a < thr);
-            gt[r] = __ballot_sync(0xffffffffu, v && a > thr);
-          }
+          const uint4 ltv = B.lt_mask[s], gtv = B.gt_mask[s];
+          const unsigned lt[4] = {ltv.x, ltv.y, ltv.z, ltv.w}, gt[4] = {gtv.x, gtv.y, gtv.z, gtv.w};
           PH_MARK(2)
           int pos = 0;
           while (pos < nvalid) {

@@ -284,3 +284,23 @@ def test_rate_sweep_bit_exact(adc, ntaps):
     assert counts.tolist() == ocounts.tolist()
     _assert_same(recs, orecs, "adc %d ntaps %d" % (adc, ntaps))
     assert counts.sum() >= 20
+
+
+def test_random_segment_tables_stress(rx, oracle):
+    """many CTAs with unequal work in flight at once: random offsets / lengths (partial rounds, segments that end
+    inside a window, back-to-back multi-round segments), repeated launches -- every record must equal the oracle's"""
+    cap = synth.make_capture(96, seed=123)
+    iq = cap["iq"].numpy()
+    L = cap["truth"]["segment_len"]
+    rng = np.random.default_rng(7)
+    for it in range(3):
+        nseg = 400
+        offs = rng.integers(0, iq.size - 3 * L, size=nseg)
+        lens = rng.integers(200, 3 * L, size=nseg)
+        lens[:40] = rng.integers(0, 700, size=40)          # tiny segments
+        segs = abi.make_segments(offs, lens)
+        recs, counts = rx.decode_capture_host(iq, segs, max_windows=8)
+        orecs, ocounts, _ = oracle.decode_segments(iq, segs, max_per_seg=8)
+        assert counts.tolist() == ocounts.tolist(), it
+        _assert_same(recs, orecs, "stress %d" % it)
+        assert counts.sum() > 400
