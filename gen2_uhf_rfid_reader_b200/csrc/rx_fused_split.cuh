@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       mbar_init(&B.tile_full[s], kWorkerWarps);
       mbar_init(&B.chain_done[s], 1);
       mbar_init(&B.elist_ready[s], 1);
-      mbar_init(&B.tile_free[s], 1);
+      mbar_init(&B.tile_free[s], 2);  // control (done with the stage's lookbacks) + chain (window emission done)
       B.n_e[s] = 0;
       B.n_ev[s] = 0;
     }
@@ -367,6 +367,11 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
   } else if (role == 0) {
     // =========================================================== chain: the exact running sums, nothing else
     float acc = 0.f;  // lane 0: avg_ampl, lane 1: dc_est.re, lane 2: dc_est.im
+    // window emission state (two tiles behind the state machine)
+    bool f_open = false, f_store = false;
+    int f_wpos = 0, n_signalled = 0, n_freed = 0, f_slot = 0, wsig_ordinal = 0;
+    float2 dc_open = make_float2(0.f, 0.f);
+    float2* win = win_base;
     PH_DECL
     for (int i = 0; i < ntiles + 2; i++) {
       const int s = i % kS;
@@ -413,7 +418,81 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       // control syncs on chain_done(i) before it publishes elist_ready(i), which this warp needs for
       // iteration i+2: never more than two arrivals outstanding => ids alternate with i
       bar2_arrive<SBAR_CHAIN_DONE>(i & 1);
+      // ---- finish tile i-2: window emission (gate_impl.cc:173,187) with the dc_est this pass just produced, and the
+      //      hand-off to the decoder
+      if (i >= 2) {
+        const int t = i - 2, ps = t % kS;
+        const float2* py = ring_y + ps * kTT;
+        const float* pe_re = etile + (ps * 2 + 0) * kTT;
+        const float* pe_im = pe_re + kTT;
+        const int pvalid = min(kTT, n_out - t * kTT);
+        const int pnev = B.n_ev[ps];
+        int pos = 0;
+        for (int e = 0; e <= pnev; e++) {
+          const bool last = e == pnev;
+          const int etype = last ? 0 : B.ev[ps][e].type;
+          const int epos = last ? pvalid : B.ev[ps][e].pos;
+          if (f_open) {
+            const int take = epos - pos;
+            if (f_store && take > 0) {
+              for (int j = lane; j < take; j += 32) win[f_wpos + j] = c_sub(py[pos + j], dc_open);
+              __threadfence_block();  // samples first, then the counter the decoder (same CTA) polls
+              __syncwarp();
+              if (lane == 0) *(volatile int*)&B.progress[f_slot] = f_wpos + take;
+            }
+            f_wpos += take;
+            pos = epos;
+          }
+          if (etype == 2) {
+            f_open = false;  // the decoder already has the window: it saw progress reach its length
+            pos = epos;
+          } else if (etype == 1) {
+            const int j = B.ev[ps][e].a;
+            dc_open = make_float2(pe_re[j], pe_im[j]);  // dc_est right after the trigger sample
+            f_store = B.ev[ps][e].c != 0;
+            f_open = true;
+            win = win_base + (B.ev[ps][e].d ? A.rn16_pad : 0);
+            if (f_store) {
+              // the scratch area and the meta slot are reused two hand-offs later
+              while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
+              f_slot = n_signalled & 1;
+              if (lane == 0) {
+                win[0] = c_sub(py[epos], dc_open);
+                const int knd = B.ev[ps][e].d;
+                B.meta_kind[f_slot] = knd; B.meta_ordinal[f_slot] = wsig_ordinal; B.meta_open[f_slot] = B.ev[ps][e].b;
+                B.meta_len[f_slot] = knd ? C.len_epc : C.len_rn16;
+                *(volatile int*)&B.progress[f_slot] = 0;
+                B.aborted[f_slot] = 0;
+              }
+              __threadfence_block();
+              __syncwarp();
+              if (lane == 0) *(volatile int*)&B.progress[f_slot] = 1;
+              // hand the window to the decoder NOW: it decodes while the gate is still open (streaming)
+              bar2_arrive<SBAR_WIN_READY>(f_slot);
+              n_signalled++;
+            }
+            wsig_ordinal++;
+            f_wpos = 1;
+            pos = epos + 1;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B.tile_free[ps]);  // second party of tile_free (control arrived after tile i-1's state machine)
+      }
     }
+    if (f_open && f_store && lane == 0) {
+      // the segment ended inside a window the decoder is already working on: let it run to the end
+      *(volatile int*)&B.aborted[f_slot] = 1;
+      __threadfence_block();
+      *(volatile int*)&B.progress[f_slot] = 1 << 30;
+    }
+    __syncwarp();
+    while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
+    if (lane == 0) {
+      B.meta_kind[n_signalled & 1] = -1;
+    }
+    __syncwarp();
+    bar2_arrive<SBAR_WIN_READY>(n_signalled & 1);
     PH_DUMP(16)
     PH_END(20)
   } else if (role == 1) {
@@ -427,16 +506,11 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
     int nq = 1;                    // n_queries_sent after START -> SEND_QUERY (reader_impl.cc:259)
     bool terminated = false;
     int closed_since = C.dc_length;
-    // emission state (two tiles behind)
-    bool f_open = false, f_store = false;
-    int f_wpos = 0, n_signalled = 0, n_freed = 0, f_slot = 0, wsig_ordinal = 0;
-    float2 dc_open = make_float2(0.f, 0.f);
-    float2* win = win_base;
     const float dclen_f = (float)C.dc_length;
     const int half_pw = C.n_PW / 2;
     PH_DECL
 
-    for (int i = 0; i < ntiles + 2; i++) {
+    for (int i = 0; i < ntiles; i++) {
       const int s = i % kS;
       PH_MARK(0)
       bar2_sync<SBAR_CHAIN_DONE>(i & 1);  // avg_ampl of tile i and dc_est of tile i-2 are final
@@ -545,83 +619,13 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         bar2_arrive<SBAR_ELIST>(i & 1);  // chain may run dc_est over this tile (its iteration i+2)
       }
       PH_MARK(3)
-      // ---- finish tile i-2: window emission (gate_impl.cc:173,187) and hand-off to the decoder
-      if (i >= 2) {
-        const int t = i - 2, ps = t % kS;
-        const float2* py = ring_y + ps * kTT;
-        const float* pe_re = etile + (ps * 2 + 0) * kTT;
-        const float* pe_im = pe_re + kTT;
-        const int pvalid = min(kTT, n_out - t * kTT);
-        const int pnev = B.n_ev[ps];
-        int pos = 0;
-        for (int e = 0; e <= pnev; e++) {
-          const bool last = e == pnev;
-          const int etype = last ? 0 : B.ev[ps][e].type;
-          const int epos = last ? pvalid : B.ev[ps][e].pos;
-          if (f_open) {
-            const int take = epos - pos;
-            if (f_store && take > 0) {
-              for (int j = lane; j < take; j += 32) win[f_wpos + j] = c_sub(py[pos + j], dc_open);
-              __threadfence_block();  // samples first, then the counter the decoder (same CTA) polls
-              __syncwarp();
-              if (lane == 0) *(volatile int*)&B.progress[f_slot] = f_wpos + take;
-            }
-            f_wpos += take;
-            pos = epos;
-          }
-          if (etype == 2) {
-            f_open = false;  // the decoder already has the window: it saw progress reach its length
-            pos = epos;
-          } else if (etype == 1) {
-            const int j = B.ev[ps][e].a;
-            dc_open = make_float2(pe_re[j], pe_im[j]);  // dc_est right after the trigger sample
-            f_store = B.ev[ps][e].c != 0;
-            f_open = true;
-            win = win_base + (B.ev[ps][e].d ? A.rn16_pad : 0);
-            if (f_store) {
-              // the scratch area and the meta slot are reused two hand-offs later
-              while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
-              f_slot = n_signalled & 1;
-              if (lane == 0) {
-                win[0] = c_sub(py[epos], dc_open);
-                const int knd = B.ev[ps][e].d;
-                B.meta_kind[f_slot] = knd; B.meta_ordinal[f_slot] = wsig_ordinal; B.meta_open[f_slot] = B.ev[ps][e].b;
-                B.meta_len[f_slot] = knd ? C.len_epc : C.len_rn16;
-                *(volatile int*)&B.progress[f_slot] = 0;
-                B.aborted[f_slot] = 0;
-              }
-              __threadfence_block();
-              __syncwarp();
-              if (lane == 0) *(volatile int*)&B.progress[f_slot] = 1;
-              // hand the window to the decoder NOW: it decodes while the gate is still open (streaming)
-              bar2_arrive<SBAR_WIN_READY>(f_slot);
-              n_signalled++;
-            }
-            wsig_ordinal++;
-            f_wpos = 1;
-            pos = epos + 1;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&B.tile_free[ps]);  // workers may refill the stage of tile i-2
-      }
+      // the ring lookbacks of tile i reach back into stage i-1 only: control is done with it (the chain
+      // warp, which emits tile i-1's window samples, is the other party of tile_free)
+      if (i >= 1 && lane == 0) mbar_arrive(&B.tile_free[(i - 1) % kS]);
       PH_MARK(4)
     }
     PH_DUMP(0)
-    if (f_open && f_store && lane == 0) {
-      // the segment ended inside a window the decoder is already working on: let it run to the end
-      *(volatile int*)&B.aborted[f_slot] = 1;
-      __threadfence_block();
-      *(volatile int*)&B.progress[f_slot] = 1 << 30;
-    }
-    __syncwarp();
-    while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
-    if (lane == 0) {
-      B.meta_kind[n_signalled & 1] = -1;
-      A.counts[seg] = wcount;
-    }
-    __syncwarp();
-    bar2_arrive<SBAR_WIN_READY>(n_signalled & 1);
+    if (lane == 0) A.counts[seg] = wcount;
     PH_END(22)
   } else {
     // =========================================================== decoder

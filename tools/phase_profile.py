@@ -25,9 +25,9 @@ rx.set_window_tap(tap)
 rx.decode_capture(cap["iq"], segs, 2)
 torch.cuda.synchronize()
 t = tap.view(torch.int64).cpu().numpy().reshape(-1)[: nseg * 24].reshape(nseg, 24)
-names = {0: ["ctl:loop", "ctl:wait_chain", "ctl:flags", "ctl:fsm+e", "ctl:emit"],
+names = {0: ["ctl:loop", "ctl:wait_chain", "ctl:flags", "ctl:fsm+e", "ctl:free"],
          8: ["wrk:loop", "wrk:wait_tma", "wrk:blocksum", "wrk:bar1", "wrk:wait_free", "wrk:y+abs", "wrk:bar2", "wrk:d,e"],
-         16: ["chn:loop", "chn:wait_full", "chn:wait_elist", "chn:chain"]}
+         16: ["chn:loop", "chn:wait_full", "chn:wait_elist", "chn:chain+flags"]}
 for base, nm in names.items():
     tot = 0
     for i, x in enumerate(nm):
