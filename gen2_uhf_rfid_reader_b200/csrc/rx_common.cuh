@@ -65,6 +65,19 @@ __device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b
 // applied where no intermediate can underflow / overflow; everything else takes the general division.
 __device__ __noinline__ float f_div_general(float x, float d) { return __fdiv_rn(x, d); }
 
+// branch-free halves of f_div_const, so that several divisions can be in flight together:
+// the multiply-correct quotient, and whether x is inside the range for which it is verified
+__device__ __forceinline__ float f_div_fast(float x, float d, float c)
+{
+  const float q = __fmul_rn(x, c);
+  return __fmaf_rn(__fmaf_rn(-q, d, x), c, q);
+}
+__device__ __forceinline__ bool f_div_fast_ok(float x)
+{
+  const float ax = fabsf(x);
+  return ax >= 7.9e-31f && ax <= 1.2e30f;
+}
+
 __device__ __forceinline__ float f_div_const(float x, float d, float c, int fast)
 {
   const float ax = fabsf(x);

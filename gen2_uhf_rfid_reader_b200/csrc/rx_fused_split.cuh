@@ -342,20 +342,47 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         const int t_hi = wt + kWorkerThreads * (kTT / kWorkerThreads - 1);  // this thread's last output of the tile
         if (t_hi >= kTT - (MFQ - 1) && t_hi < nvalid) bhist[t_hi - (kTT - (MFQ - 1))] = b_keep;
       }
+      {
+        // ring differences of this thread's samples, all divisions in flight together (gate_impl.cc:131,141); the
+        // multiply-correct quotients are used when every input of the warp is inside the verified range
+        float xd[kTT / kWorkerThreads], xr[kTT / kWorkerThreads], xi[kTT / kWorkerThreads];
+        bool all_ok = C.win_div_fast && C.dc_div_fast;
 #pragma unroll
-      for (int r = 0; r < kTT / kWorkerThreads; r++) {
-        const int t = wt + r * kWorkerThreads;
-        if (t < nvalid) {
-          const float a_cur = a_reg[r];
-          const float2 y_cur = y_reg[r];
-          int ia = ts * kTT + t - C.win_length;
-          if (ia < 0) ia += kRing;
-          ring_d[ts * kTT + t] = f_div_const(f_sub(a_cur, ring_a[ia]), winlen_f, C.win_recip, C.win_div_fast);  // gate_impl.cc:131
-          int iy = ts * kTT + t - C.dc_length;
-          if (iy < 0) iy += kRing;
-          const float2 old = ring_y[iy];
-          etile[(ts * 2 + 0) * kTT + t] = f_div_const(f_sub(y_cur.x, old.x), dclen_f, C.dc_recip, C.dc_div_fast);  // gate_impl.cc:141, if time-contiguous
-          etile[(ts * 2 + 1) * kTT + t] = f_div_const(f_sub(y_cur.y, old.y), dclen_f, C.dc_recip, C.dc_div_fast);
+        for (int r = 0; r < kTT / kWorkerThreads; r++) {
+          const int t = wt + r * kWorkerThreads;
+          xd[r] = xr[r] = xi[r] = 1.0f;
+          if (t < nvalid) {
+            int ia = ts * kTT + t - C.win_length;
+            if (ia < 0) ia += kRing;
+            int iy = ts * kTT + t - C.dc_length;
+            if (iy < 0) iy += kRing;
+            const float2 old = ring_y[iy];
+            xd[r] = f_sub(a_reg[r], ring_a[ia]);
+            xr[r] = f_sub(y_reg[r].x, old.x);
+            xi[r] = f_sub(y_reg[r].y, old.y);
+          }
+          all_ok = all_ok && f_div_fast_ok(xd[r]) && f_div_fast_ok(xr[r]) && f_div_fast_ok(xi[r]);
+        }
+        if (__all_sync(0xffffffffu, all_ok)) {
+#pragma unroll
+          for (int r = 0; r < kTT / kWorkerThreads; r++) {
+            const int t = wt + r * kWorkerThreads;
+            if (t < nvalid) {
+              ring_d[ts * kTT + t] = f_div_fast(xd[r], winlen_f, C.win_recip);
+              etile[(ts * 2 + 0) * kTT + t] = f_div_fast(xr[r], dclen_f, C.dc_recip);
+              etile[(ts * 2 + 1) * kTT + t] = f_div_fast(xi[r], dclen_f, C.dc_recip);
+            }
+          }
+        } else {  // an exact zero, a denormal, or an unverified divisor somewhere in the warp: IEEE division
+#pragma unroll
+          for (int r = 0; r < kTT / kWorkerThreads; r++) {
+            const int t = wt + r * kWorkerThreads;
+            if (t < nvalid) {
+              ring_d[ts * kTT + t] = f_div_const(xd[r], winlen_f, C.win_recip, C.win_div_fast);
+              etile[(ts * 2 + 0) * kTT + t] = f_div_const(xr[r], dclen_f, C.dc_recip, C.dc_div_fast);
+              etile[(ts * 2 + 1) * kTT + t] = f_div_const(xi[r], dclen_f, C.dc_recip, C.dc_div_fast);
+            }
+          }
         }
       }
       __syncwarp();
