@@ -38,6 +38,7 @@
 #undef private
 #else
 #include "gate_impl.h"
+#include "matched_filter_impl.h"
 #include "reader_impl.h"
 #include "tag_decoder_impl.h"
 #endif
@@ -245,8 +246,30 @@ __attribute__((visibility("default"))) int gen2flow_run_stream(
     float* tx, size_t tx_cap, size_t* tx_n, float* y_out)
 {
   if (!iq_raw || decim <= 0 || ntaps <= 0 || chunk <= 0) return -1;
-  std::vector<gr_complex> y(n_raw / (size_t)decim + 1);
-  size_t ny = oracle_mf_boxcar(iq_raw, n_raw, ntaps, decim, (float*)y.data());
+  std::vector<gr_complex> y(n_raw / (size_t)decim + 2);
+  size_t ny = 0;
+#ifdef DRIVE_REFERENCE
+  ny = oracle_mf_boxcar(iq_raw, n_raw, ntaps, decim, (float*)y.data());
+#else
+  {
+    /* this repo's matched-filter host block (GPU) stands where fir_filter_ccc stands in apps/reader.py:75;
+     * it is fed in scheduler-sized chunks like the other blocks */
+    matched_filter::sptr M = matched_filter::make(decim, ntaps);
+    size_t pos_in = 0;
+    const int in_chunk = chunk * decim;
+    while (pos_in < n_raw) {
+      int nin = (int)std::min((size_t)in_chunk, n_raw - pos_in);
+      if (nin < decim) break; /* an incomplete decimation group at the very end produces nothing */
+      gr_vector_int ni(1, nin);
+      gr_vector_const_void_star iv(1, (const void*)(iq_raw + 2 * pos_in));
+      gr_vector_void_star ov(1, (void*)(y.data() + ny));
+      M->shim_reset_counts();
+      int w = M->general_work(chunk + 1, ni, iv, ov);
+      pos_in += (size_t)M->shim_consumed();
+      ny += (size_t)w;
+    }
+  }
+#endif
   if (y_out) memcpy(y_out, y.data(), ny * sizeof(gr_complex));
   std::vector<float> txv;
   std::string text;
