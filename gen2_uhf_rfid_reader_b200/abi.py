@@ -44,6 +44,13 @@ class Stats(C.Structure):
         return {int(self.tag_id[i]): int(self.tag_reads[i]) for i in range(n)}
 
 
+class Segmenter(C.Structure):
+    """rfid_b200_segmenter (include/rfid_b200.h): CW-gap segmenter settings."""
+    _fields_ = [("level_frac", C.c_float), ("gap_us", C.c_float), ("lead_us", C.c_float),
+                ("min_pulses", C.c_int32), ("commands_per_segment", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+assert C.sizeof(Segmenter) == 32
 assert C.sizeof(WindowResult) == 64
 assert C.sizeof(Segment) == 16
 assert C.sizeof(Params) == 32

@@ -68,6 +68,12 @@ def load_library():
     L.rfid_b200_decoder_work.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
     L.rfid_b200_mf_work.restype = C.c_int
     L.rfid_b200_mf_work.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip]
+    L.rfid_b200_default_segmenter.argtypes = [C.POINTER(abi.Segmenter)]
+    L.rfid_b200_segment_capture.restype = C.c_int
+    L.rfid_b200_segment_capture.argtypes = [vp, vp, C.c_size_t, C.POINTER(abi.Segmenter), vp, C.c_int, ip, vp]
+    L.rfid_b200_ingest_capture_host.restype = C.c_int
+    L.rfid_b200_ingest_capture_host.argtypes = [vp, vp, C.c_size_t, C.POINTER(abi.Segmenter), C.c_int, vp, C.c_int, ip,
+                                                vp, vp]
     _lib = L
     return L
 
@@ -78,7 +84,16 @@ EXPORTED_SYMBOLS = [
     "rfid_b200_decode_capture", "rfid_b200_decode_capture_host", "rfid_b200_last_launch_count",
     "rfid_b200_kernel_time", "rfid_b200_enable_kernel_timing", "rfid_b200_set_window_tap",
     "rfid_b200_reduce_stats", "rfid_b200_gate_work", "rfid_b200_decoder_work", "rfid_b200_mf_work",
+    "rfid_b200_default_segmenter", "rfid_b200_segment_capture", "rfid_b200_ingest_capture_host",
 ]
+
+
+def default_segmenter(**kw):
+    sp = abi.Segmenter()
+    load_library().rfid_b200_default_segmenter(C.byref(sp))
+    for k, v in kw.items():
+        setattr(sp, k, type(getattr(sp, k))(v))
+    return sp
 
 
 def default_params(**kw):
@@ -154,6 +169,36 @@ class Gen2Rx:
         """Same call on raw (e.g. pinned) host pointers: no Python-side copies."""
         rc = self.lib.rfid_b200_decode_capture_host(self.h, iq_ptr, n_raw, segs_ptr, nseg, max_windows, res_ptr, cnt_ptr)
         self._ck(rc, "rfid_b200_decode_capture_host")
+
+    # ---------------------------------------------------------------- capture ingest
+    def segment_capture(self, iq, segmenter=None, capacity=None, stream=None):
+        """CW-gap segment table (SEGMENT_DTYPE ndarray) of a CUDA capture tensor."""
+        import torch
+        n_raw = iq.numel() if iq.is_complex() else iq.numel() // 2
+        cap = int(capacity) if capacity is not None else max(16, n_raw // 4096)
+        segs = np.zeros(cap, dtype=abi.SEGMENT_DTYPE)
+        n = C.c_int(0)
+        s = stream if stream is not None else torch.cuda.current_stream(iq.device)
+        rc = self.lib.rfid_b200_segment_capture(self.h, iq.data_ptr(), n_raw, C.byref(segmenter) if segmenter else None,
+                                                segs.ctypes.data, cap, C.byref(n), s.cuda_stream)
+        self._ck(rc, "rfid_b200_segment_capture")
+        return segs[:n.value].copy()
+
+    def ingest_capture_host(self, iq, segmenter=None, max_windows=4, capacity=None):
+        """Recorded capture (host complex64 ndarray, e.g. np.fromfile/np.memmap) -> (segs, records, counts)."""
+        raw = np.ascontiguousarray(iq).view(np.float32).ravel()
+        n_raw = raw.size // 2
+        cap = int(capacity) if capacity is not None else max(16, n_raw // 4096)
+        segs = np.zeros(cap, dtype=abi.SEGMENT_DTYPE)
+        recs = np.zeros((cap, max_windows), dtype=abi.RESULT_DTYPE)
+        counts = np.zeros(cap, dtype=np.int32)
+        n = C.c_int(0)
+        rc = self.lib.rfid_b200_ingest_capture_host(self.h, raw.ctypes.data, n_raw, C.byref(segmenter) if segmenter else None,
+                                                    max_windows, segs.ctypes.data, cap, C.byref(n), recs.ctypes.data,
+                                                    counts.ctypes.data)
+        self._ck(rc, "rfid_b200_ingest_capture_host")
+        k = n.value
+        return segs[:k].copy(), recs[:k].copy(), counts[:k].copy()
 
     def set_window_tap(self, tensor_or_none):
         ptr = tensor_or_none.data_ptr() if tensor_or_none is not None else None

@@ -2,6 +2,7 @@
 // Host side: context, configuration derivation, launches, host<->device marshalling,
 // READER_STATS reduction.  There is no CPU implementation of the signal path in this
 // library: every entry point that produces samples or decisions launches a kernel.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 #include "rx_common.cuh"
 #include "rx_fused.cuh"
 #include "rx_fused_split.cuh"
+#include "rx_ingest.cuh"
 
 using namespace rfid_b200;
 
@@ -48,6 +50,13 @@ struct rfid_b200_ctx {
   rfid_b200_window_result* d_one;
   // mf block mode
   void* d_mf; size_t d_mf_bytes; long long mf_abs0; long long mf_have; long long mf_next_n;
+  // capture ingest (segmenter work buffers, pinned upload staging)
+  void* d_mask; size_t d_mask_bytes;
+  void* d_chunk; size_t d_chunk_bytes;  // chunk_last | prev_low | falls_before | chunk_falls
+  void* d_bursts; size_t d_bursts_bytes;
+  void* d_ing;  // level partials + totals
+  void* h_stage[2]; cudaEvent_t ev_stage[2];
+  std::vector<IngestBurst> h_bursts;
 };
 
 namespace {
@@ -255,6 +264,9 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
   ctx->d_iq_bytes = ctx->d_segs_bytes = ctx->d_res_bytes = ctx->d_cnt_bytes = ctx->d_in_bytes = ctx->d_out_bytes = ctx->d_m2_bytes = ctx->d_mf_bytes = 0;
   ctx->d_gate = nullptr; ctx->d_gate_out = nullptr; ctx->d_one = nullptr;
   ctx->mf_abs0 = 0; ctx->mf_have = 0; ctx->mf_next_n = 0;
+  ctx->d_mask = ctx->d_chunk = ctx->d_bursts = ctx->d_ing = nullptr;
+  ctx->d_mask_bytes = ctx->d_chunk_bytes = ctx->d_bursts_bytes = 0;
+  ctx->h_stage[0] = ctx->h_stage[1] = nullptr; ctx->ev_stage[0] = ctx->ev_stage[1] = nullptr;
   memset(&ctx->layout, 0, sizeof(ctx->layout));
   make_layout(cfg, ctx->layout);
   cudaError_t e = cudaSetDevice(p->device);
@@ -294,9 +306,13 @@ void rfid_b200_destroy(rfid_b200_ctx* ctx)
   cudaSetDevice(ctx->device);
   drain_timing(ctx);
   void* ptrs[] = {ctx->d_win, ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
-                  ctx->d_gate, ctx->d_gate_out, ctx->d_one};
+                  ctx->d_gate, ctx->d_gate_out, ctx->d_one, ctx->d_mask, ctx->d_chunk, ctx->d_bursts, ctx->d_ing};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int b = 0; b < 2; b++) {
+    if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+    if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
+  }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -457,6 +473,270 @@ int rfid_b200_reduce_stats(const rfid_b200_ctx* ctx, const rfid_b200_window_resu
     out->tag_reads[k] = kv.second;
     k++;
   }
+  return RFID_B200_OK;
+}
+
+// ------------------------------------------------------------------ capture ingest
+}  // extern "C"
+
+namespace {
+
+constexpr size_t kUploadSamples = (size_t)1 << 21;  // 16 MiB per upload slice; multiple of kIngestChunk
+constexpr size_t kLevelHead = (size_t)1 << 21;      // CW level is estimated on the head of the capture
+
+struct SegmenterCfg {
+  float level_frac;
+  unsigned int gap, lead;
+  int min_pulses, commands;
+};
+
+int resolve_segmenter(const rfid_b200_ctx* ctx, const rfid_b200_segmenter* sp, SegmenterCfg& o)
+{
+  rfid_b200_segmenter d;
+  rfid_b200_default_segmenter(&d);
+  if (sp) d = *sp;
+  if (!(d.level_frac > 0.f && d.level_frac < 1.f) || !(d.gap_us > 0.f) || !(d.lead_us >= 0.f) || d.min_pulses < 1 ||
+      d.commands_per_segment < 1)
+    return RFID_B200_EINVAL;
+  o.level_frac = d.level_frac;
+  o.gap = (unsigned int)((double)d.gap_us * 1e-6 * ctx->cfg.adc_rate);
+  o.lead = (unsigned int)((double)d.lead_us * 1e-6 * ctx->cfg.adc_rate);
+  if (o.gap < 1) o.gap = 1;
+  if (o.lead >= o.gap) return RFID_B200_EINVAL;  // a lead-in must not reach into the previous command
+  o.min_pulses = d.min_pulses;
+  o.commands = d.commands_per_segment;
+  return RFID_B200_OK;
+}
+
+int ingest_alloc(rfid_b200_ctx* ctx, size_t n_raw, const SegmenterCfg& sc, long long& n_chunks, unsigned int& burst_cap)
+{
+  n_chunks = (long long)((n_raw + kIngestChunk - 1) / kIngestChunk);
+  burst_cap = (unsigned int)(n_raw / sc.gap + 4);
+  int rc;
+  if ((rc = grow(ctx, &ctx->d_mask, &ctx->d_mask_bytes, (size_t)n_chunks * 32 * 4))) return rc;
+  if ((rc = grow(ctx, &ctx->d_chunk, &ctx->d_chunk_bytes, (size_t)n_chunks * 28 + 64))) return rc;
+  if ((rc = grow(ctx, &ctx->d_bursts, &ctx->d_bursts_bytes, (size_t)burst_cap * sizeof(IngestBurst)))) return rc;
+  if (!ctx->d_ing) {
+    if (cudaMalloc(&ctx->d_ing, kLevelBlocks * sizeof(double) + sizeof(IngestTotals)) != cudaSuccess) {
+      cudaGetLastError();
+      return RFID_B200_ENOMEM;
+    }
+  }
+  return RFID_B200_OK;
+}
+
+struct IngestPtrs {
+  double* partial; IngestTotals* tot;
+  unsigned int* mask; long long* chunk_last; long long* prev_low; unsigned long long* falls_before; unsigned int* chunk_falls;
+};
+
+IngestPtrs ingest_ptrs(rfid_b200_ctx* ctx, long long n_chunks)
+{
+  IngestPtrs P;
+  P.partial = reinterpret_cast<double*>(ctx->d_ing);
+  P.tot = reinterpret_cast<IngestTotals*>(P.partial + kLevelBlocks);
+  P.mask = reinterpret_cast<unsigned int*>(ctx->d_mask);
+  P.chunk_last = reinterpret_cast<long long*>(ctx->d_chunk);
+  P.prev_low = P.chunk_last + n_chunks;
+  P.falls_before = reinterpret_cast<unsigned long long*>(P.prev_low + n_chunks);
+  P.chunk_falls = reinterpret_cast<unsigned int*>(P.falls_before + n_chunks);
+  return P;
+}
+
+int launch_level(rfid_b200_ctx* ctx, const float2* d_iq, size_t n_raw, const SegmenterCfg& sc, const IngestPtrs& P, cudaStream_t s)
+{
+  const unsigned long long n0 = n_raw < kLevelHead ? n_raw : kLevelHead;
+  ingest_level_partial<<<kLevelBlocks, kLevelThreads, 0, s>>>(d_iq, n0, P.partial);
+  ingest_level_final<<<1, 32, 0, s>>>(P.partial, n0, sc.level_frac, P.tot);
+  CK(cudaGetLastError());
+  ctx->last_launches += 2;
+  return RFID_B200_OK;
+}
+
+int launch_mask(rfid_b200_ctx* ctx, const float2* d_iq, size_t n_raw, long long first_chunk, long long n, const IngestPtrs& P,
+                cudaStream_t s)
+{
+  if (n <= 0) return RFID_B200_OK;
+  long long blocks = (n + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ingest_mask<<<(unsigned)blocks, 256, 0, s>>>(d_iq, n_raw, first_chunk, n, P.tot, P.mask, P.chunk_last, P.chunk_falls);
+  CK(cudaGetLastError());
+  ctx->last_launches += 1;
+  return RFID_B200_OK;
+}
+
+// scan + burst extraction + copy back; synchronises `s`
+int finish_bursts(rfid_b200_ctx* ctx, long long n_chunks, unsigned int burst_cap, const SegmenterCfg& sc, const IngestPtrs& P,
+                  cudaStream_t s, IngestTotals& tot)
+{
+  ingest_scan<<<1, 1024, 0, s>>>(n_chunks, P.chunk_last, P.chunk_falls, P.prev_low, P.falls_before, P.tot);
+  long long blocks = (n_chunks + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ingest_bursts<<<(unsigned)blocks, 256, 0, s>>>(n_chunks, P.mask, P.prev_low, P.falls_before, sc.gap,
+                                                 reinterpret_cast<IngestBurst*>(ctx->d_bursts), burst_cap, P.tot);
+  CK(cudaGetLastError());
+  ctx->last_launches += 2;
+  CK(cudaMemcpyAsync(&tot, P.tot, sizeof(tot), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (tot.n_bursts > burst_cap) { ctx->last_error = "segmenter: burst list overflow"; return RFID_B200_ECAPACITY; }
+  ctx->h_bursts.resize(tot.n_bursts);
+  if (tot.n_bursts) {
+    CK(cudaMemcpyAsync(ctx->h_bursts.data(), ctx->d_bursts, (size_t)tot.n_bursts * sizeof(IngestBurst), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  std::sort(ctx->h_bursts.begin(), ctx->h_bursts.end(), [](const IngestBurst& a, const IngestBurst& b) { return a.pos < b.pos; });
+  return RFID_B200_OK;
+}
+
+// Pair commands into segments.  Segment j covers commands [j*C, (j+1)*C): it starts `lead` samples before its
+// first command (rounded down to a multiple of decim so the matched filter keeps the capture's decimation
+// phase; the first segment starts at sample 0 like the reference's continuous run) and runs up to the first
+// pulse of the next segment's first command, i.e. consecutive segments overlap by the lead-in.
+int build_segments(const rfid_b200_ctx* ctx, const std::vector<IngestBurst>& b, unsigned long long n_falls, size_t n_raw,
+                   const SegmenterCfg& sc, rfid_b200_segment* out, int capacity, int* nseg)
+{
+  std::vector<unsigned long long> cmd;
+  for (size_t k = 0; k < b.size(); k++) {
+    const unsigned long long next_rank = k + 1 < b.size() ? b[k + 1].rank : n_falls;
+    if (next_rank - b[k].rank >= (unsigned long long)sc.min_pulses) cmd.push_back(b[k].pos);
+  }
+  const size_t C = (size_t)sc.commands;
+  const size_t ns = cmd.empty() ? (n_raw ? 1 : 0) : (cmd.size() + C - 1) / C;
+  *nseg = (int)ns;
+  if ((int)ns > capacity) return RFID_B200_ECAPACITY;
+  const unsigned long long D = (unsigned long long)ctx->cfg.decim;
+  for (size_t j = 0; j < ns; j++) {
+    unsigned long long start = 0;
+    if (j > 0) {
+      const unsigned long long c0 = cmd[j * C];
+      start = c0 > sc.lead ? c0 - sc.lead : 0;
+      start -= start % D;
+    }
+    const unsigned long long end = (j + 1) * C < cmd.size() ? cmd[(j + 1) * C] : (unsigned long long)n_raw;
+    if (end - start > 0xffffffffull) return RFID_B200_EINVAL;
+    out[j].offset = start;
+    out[j].length = (uint32_t)(end - start);
+    out[j].reserved = 0;
+  }
+  return RFID_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void rfid_b200_default_segmenter(rfid_b200_segmenter* sp)
+{
+  if (!sp) return;
+  memset(sp, 0, sizeof(*sp));
+  sp->level_frac = 0.5f;
+  sp->gap_us = 400.f;
+  sp->lead_us = 300.f;
+  sp->min_pulses = kNumPulsesCommand + 1;  // gate_impl.cc:164: num_pulses > NUM_PULSES_COMMAND
+  sp->commands_per_segment = 2;            // RN16 window + EPC window
+}
+
+int rfid_b200_segment_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw, const rfid_b200_segmenter* sp,
+                              rfid_b200_segment* h_segs, int capacity, int* nseg, void* stream)
+{
+  if (!ctx || !d_iq || !h_segs || !nseg || capacity < 0) return RFID_B200_EINVAL;
+  *nseg = 0;
+  SegmenterCfg sc;
+  int rc = resolve_segmenter(ctx, sp, sc);
+  if (rc) return rc;
+  if (n_raw == 0) return RFID_B200_OK;
+  CK(cudaSetDevice(ctx->device));
+  long long n_chunks;
+  unsigned int burst_cap;
+  if ((rc = ingest_alloc(ctx, n_raw, sc, n_chunks, burst_cap))) return rc;
+  const IngestPtrs P = ingest_ptrs(ctx, n_chunks);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float2* iq = reinterpret_cast<const float2*>(d_iq);
+  ctx->last_launches = 0;
+  if ((rc = launch_level(ctx, iq, n_raw, sc, P, s))) return rc;
+  if ((rc = launch_mask(ctx, iq, n_raw, 0, n_chunks, P, s))) return rc;
+  IngestTotals tot;
+  if ((rc = finish_bursts(ctx, n_chunks, burst_cap, sc, P, s, tot))) return rc;
+  return build_segments(ctx, ctx->h_bursts, tot.n_falls, n_raw, sc, h_segs, capacity, nseg);
+}
+
+int rfid_b200_ingest_capture_host(rfid_b200_ctx* ctx, const float* h_iq, size_t n_raw, const rfid_b200_segmenter* sp,
+                                  int max_windows_per_segment, rfid_b200_segment* h_segs, int seg_capacity, int* nseg,
+                                  rfid_b200_window_result* h_results, int32_t* h_counts)
+{
+  if (!ctx || !h_iq || !h_segs || !nseg || !h_results || !h_counts || seg_capacity < 0 || max_windows_per_segment < 1)
+    return RFID_B200_EINVAL;
+  *nseg = 0;
+  SegmenterCfg sc;
+  int rc = resolve_segmenter(ctx, sp, sc);
+  if (rc) return rc;
+  if (n_raw == 0) return RFID_B200_OK;
+  if (!pick_kernel(ctx->cfg)) { ctx->last_error = "capture mode supports decim = 5 only in this build"; return RFID_B200_EINVAL; }
+  CK(cudaSetDevice(ctx->device));
+  long long n_chunks;
+  unsigned int burst_cap;
+  if ((rc = ingest_alloc(ctx, n_raw, sc, n_chunks, burst_cap))) return rc;
+  if ((rc = grow(ctx, &ctx->d_iq, &ctx->d_iq_bytes, n_raw * 8 + 16))) return rc;
+  const IngestPtrs P = ingest_ptrs(ctx, n_chunks);
+  cudaStream_t s = ctx->stream;
+  const float2* d_iq = reinterpret_cast<const float2*>(ctx->d_iq);
+
+  // pageable sources go through two pinned staging slices so the host memcpy of slice k+1 overlaps the DMA of
+  // slice k; pinned (registered) sources are DMA'd directly.  The threshold pass runs behind each slice.
+  cudaPointerAttributes attr;
+  bool pinned = cudaPointerGetAttributes(&attr, h_iq) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) {
+    for (int b = 0; b < 2; b++) {
+      if (!ctx->h_stage[b]) {
+        if (cudaHostAlloc(&ctx->h_stage[b], kUploadSamples * 8, cudaHostAllocDefault) != cudaSuccess) {
+          cudaGetLastError();
+          return RFID_B200_ENOMEM;
+        }
+        CK(cudaEventCreateWithFlags(&ctx->ev_stage[b], cudaEventDisableTiming));
+      }
+    }
+  }
+  ctx->last_launches = 0;
+  int launches = 0;
+  size_t slice = 0;
+  for (size_t off = 0; off < n_raw; off += kUploadSamples, slice++) {
+    const size_t n = n_raw - off < kUploadSamples ? n_raw - off : kUploadSamples;
+    const float* src = h_iq + 2 * off;
+    if (!pinned) {
+      const int b = (int)(slice & 1);
+      if (slice >= 2) CK(cudaEventSynchronize(ctx->ev_stage[b]));
+      memcpy(ctx->h_stage[b], src, n * 8);
+      CK(cudaMemcpyAsync((char*)ctx->d_iq + off * 8, ctx->h_stage[b], n * 8, cudaMemcpyHostToDevice, s));
+      CK(cudaEventRecord(ctx->ev_stage[b], s));
+    } else {
+      CK(cudaMemcpyAsync((char*)ctx->d_iq + off * 8, src, n * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (off == 0 && (rc = launch_level(ctx, d_iq, n_raw, sc, P, s))) return rc;
+    const long long first = (long long)(off / kIngestChunk);
+    const long long cnt = (long long)((n + kIngestChunk - 1) / kIngestChunk);
+    // the mask kernel treats samples beyond `off + n` as not yet present: pass the uploaded extent as n_raw
+    if ((rc = launch_mask(ctx, d_iq, off + n, first, cnt, P, s))) return rc;
+  }
+  IngestTotals tot;
+  if ((rc = finish_bursts(ctx, n_chunks, burst_cap, sc, P, s, tot))) return rc;
+  launches = ctx->last_launches;
+  if ((rc = build_segments(ctx, ctx->h_bursts, tot.n_falls, n_raw, sc, h_segs, seg_capacity, nseg))) return rc;
+  const int ns = *nseg;
+  if (ns == 0) return RFID_B200_OK;
+  const size_t res_bytes = (size_t)ns * max_windows_per_segment * sizeof(rfid_b200_window_result);
+  if ((rc = grow(ctx, &ctx->d_segs, &ctx->d_segs_bytes, (size_t)ns * sizeof(rfid_b200_segment)))) return rc;
+  if ((rc = grow(ctx, &ctx->d_res, &ctx->d_res_bytes, res_bytes))) return rc;
+  if ((rc = grow(ctx, &ctx->d_cnt, &ctx->d_cnt_bytes, (size_t)ns * 4))) return rc;
+  CK(cudaMemcpyAsync(ctx->d_segs, h_segs, (size_t)ns * sizeof(rfid_b200_segment), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ctx->d_res, 0, res_bytes, s));
+  rc = rfid_b200_decode_capture(ctx, (const float*)ctx->d_iq, n_raw, (const rfid_b200_segment*)ctx->d_segs, ns,
+                                max_windows_per_segment, (rfid_b200_window_result*)ctx->d_res, (int32_t*)ctx->d_cnt, s);
+  if (rc) return rc;
+  ctx->last_launches += launches;
+  CK(cudaMemcpyAsync(h_results, ctx->d_res, res_bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_counts, ctx->d_cnt, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return RFID_B200_OK;
 }
 

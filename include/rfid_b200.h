@@ -167,6 +167,46 @@ RFID_B200_API int rfid_b200_reduce_stats(const rfid_b200_ctx* ctx, const rfid_b2
                                          const int32_t* h_counts, int nseg, int max_windows_per_segment,
                                          int continuous, rfid_b200_stats* out);
 
+/* ---------------- capture ingest ----------------
+ * The reference decodes a recorded file (apps/reader.py:101-112, format: raw interleaved
+ * float32 I,Q, misc/code/plot_signal.m:5-9) through ONE sequential gate.  Capture mode wants
+ * independent segments, so a recording is first cut where nothing happens: reader commands are
+ * bursts of low pulses (PW = 12 us, reader_impl.cc:55-71) separated by CW; every burst with more
+ * than NUM_PULSES_COMMAND pulses arms exactly one gate window (gate_impl.cc:150-180) and the
+ * window kinds alternate RN16/EPC, so a segment = `commands_per_segment` consecutive commands
+ * plus the CW after each, starting `lead_us` of CW before the first.  Segment offsets are
+ * multiples of `decim` (the matched filter keeps the capture's decimation phase); segment 0
+ * starts at sample 0.  Decoding the segments reproduces the continuous reference run bit for
+ * bit in every decision (open index, sync index, T, bits, CRC); correlation scores agree to the
+ * drift of the reference's float running means. */
+typedef struct rfid_b200_segmenter {
+  float level_frac;             /* low when |x| < level_frac * (mean |x| of the first 2^21 samples); 0.5 */
+  float gap_us;                 /* CW longer than this separates two commands; 400 (> TRcal = 200 us) */
+  float lead_us;                /* CW kept in front of a segment's first command; 300 (< gap_us) */
+  int32_t min_pulses;           /* bursts with fewer low pulses are not commands; 6 (gate_impl.cc:164) */
+  int32_t commands_per_segment; /* 2: one RN16 window + one EPC window */
+  int32_t reserved[3];
+} rfid_b200_segmenter;
+
+RFID_B200_API void rfid_b200_default_segmenter(rfid_b200_segmenter* sp);
+
+/* Segment table of a capture that is already in device memory.  sp may be NULL (defaults).
+ * h_segs: HOST array of `capacity` entries; *nseg receives the number of segments (also when
+ * RFID_B200_ECAPACITY is returned).  Runs on `stream` and synchronises it. */
+RFID_B200_API int rfid_b200_segment_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw,
+                                            const rfid_b200_segmenter* sp, rfid_b200_segment* h_segs,
+                                            int capacity, int* nseg, void* stream);
+
+/* File-to-records ingest, HOST pointers: uploads the capture in 16 MiB slices (pageable memory
+ * through two pinned staging buffers, registered/pinned memory directly) with the threshold
+ * pass of the segmenter running behind each slice, builds the segment table, decodes it and
+ * copies table, records and counts back.  h_results holds seg_capacity*max_windows_per_segment
+ * records, h_counts seg_capacity ints. */
+RFID_B200_API int rfid_b200_ingest_capture_host(rfid_b200_ctx* ctx, const float* h_iq, size_t n_raw,
+                                                const rfid_b200_segmenter* sp, int max_windows_per_segment,
+                                                rfid_b200_segment* h_segs, int seg_capacity, int* nseg,
+                                                rfid_b200_window_result* h_results, int32_t* h_counts);
+
 /* ---------------- block mode (GNU Radio drop-in) ----------------
  * Called from the thin host blocks' general_work(); HOST pointers, owned by the
  * scheduler, touched only during the call.  State lives in the context (device

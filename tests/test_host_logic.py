@@ -135,3 +135,35 @@ def test_constant_division_sequence_is_exact_for_every_float():
     os.unlink(exe)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count(": 0 mismatches") == len(divs)
+
+
+# ------------------------------------------------------------------ capture ingest: segmentation rule (CPU model)
+def test_segmenter_rule_on_golden_recording(cfg1_iq, cfg1_golden):
+    """the CW-gap rule on the reference's recording: 72 Queries + 71 ACKs found, one stray burst rejected,
+    every golden window lies inside exactly the segment that holds its command"""
+    import segmenter_model as sm
+    pos, pulses = sm.bursts(cfg1_iq)
+    assert sorted(set(pulses.tolist())) == [3, 21, 26]          # stray pulses, ACK (21), Query (26)
+    segs, cmd = sm.segment_table(cfg1_iq)
+    assert len(cmd) == 143 and len(segs) == 72
+    assert all(off % 5 == 0 for off, _ in segs) and segs[0][0] == 0
+    assert segs[-1][0] + segs[-1][1] == cfg1_iq.size
+    opens = cfg1_golden["open_index"].astype(np.int64) * 5      # raw index of every golden window
+    ends = opens + cfg1_golden["length"].astype(np.int64) * 5
+    for k in range(142):
+        off, ln = segs[k // 2]
+        assert off < opens[k] and ends[k] <= off + ln, k
+        # the window belongs to command k: it opens after that command and before the next one
+        assert cmd[k] < opens[k] and (k + 1 >= len(cmd) or ends[k] < cmd[k + 1])
+
+
+def test_segmenter_rule_on_synthetic_capture():
+    import segmenter_model as sm
+    cap = synth.make_capture(24, seed=3)
+    iq = cap["iq"].numpy()
+    segs, cmd = sm.segment_table(iq)
+    assert len(segs) == 24 and len(cmd) == 48
+    gen = cap["segments"]
+    for (off, ln), g in zip(segs, gen):
+        # segmenter's cut lies in the generator's lead-in CW of the same round
+        assert int(g["offset"]) <= off + 1200 and off < int(g["offset"]) + int(g["length"])
