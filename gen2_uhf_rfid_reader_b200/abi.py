@@ -50,6 +50,23 @@ class Segmenter(C.Structure):
                 ("min_pulses", C.c_int32), ("commands_per_segment", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
+class TxCommand(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("arg", C.c_int32)]
+
+
+class SimParams(C.Structure):
+    """rfid_b200_sim_params (include/rfid_b200.h): inventory-slot simulator settings."""
+    _fields_ = [("seed", C.c_uint64), ("n_tags", C.c_int32), ("closed_loop", C.c_int32), ("dac_rate", C.c_int32),
+                ("segment_us", C.c_float), ("lead_us", C.c_float), ("noise_sigma", C.c_float), ("tag_gain", C.c_float),
+                ("tag_phase", C.c_float), ("clock_pct", C.c_float), ("leak_re", C.c_float), ("leak_im", C.c_float),
+                ("floor_level", C.c_float), ("reserved", C.c_int32 * 2)]
+
+
+TX_START, TX_QUERY, TX_QUERY_REP, TX_ACK, TX_CW, TX_NAK, TX_POWER_DOWN, TX_QUERY_ADJUST = range(8)
+TX_COMMAND_DTYPE = np.dtype([("kind", "<i4"), ("arg", "<i4")])
+SIM_TRUTH_DTYPE = np.dtype([("is_query", "<i4"), ("n_replies", "<i4"), ("strongest_rn16", "<i4"), ("acked_rn16", "<i4"),
+                            ("replier", "<i4"), ("reserved", "<i4", (3,)), ("epc", "u1", (16,))])
+assert C.sizeof(SimParams) == 64 and SIM_TRUTH_DTYPE.itemsize == 48 and C.sizeof(TxCommand) == 8
 assert C.sizeof(Segmenter) == 32
 assert C.sizeof(WindowResult) == 64
 assert C.sizeof(Segment) == 16

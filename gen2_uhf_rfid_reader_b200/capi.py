@@ -74,6 +74,13 @@ def load_library():
     L.rfid_b200_ingest_capture_host.restype = C.c_int
     L.rfid_b200_ingest_capture_host.argtypes = [vp, vp, C.c_size_t, C.POINTER(abi.Segmenter), C.c_int, vp, C.c_int, ip,
                                                 vp, vp]
+    L.rfid_b200_tx_synth.restype = C.c_int
+    L.rfid_b200_tx_synth.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]
+    L.rfid_b200_default_sim.argtypes = [C.POINTER(abi.SimParams)]
+    L.rfid_b200_sim_segment_length.restype = C.c_int
+    L.rfid_b200_sim_segment_length.argtypes = [vp, C.POINTER(abi.SimParams)]
+    L.rfid_b200_sim_capture.restype = C.c_int
+    L.rfid_b200_sim_capture.argtypes = [vp, C.POINTER(abi.SimParams), C.c_int64, C.c_int, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -85,7 +92,16 @@ EXPORTED_SYMBOLS = [
     "rfid_b200_kernel_time", "rfid_b200_enable_kernel_timing", "rfid_b200_set_window_tap",
     "rfid_b200_reduce_stats", "rfid_b200_gate_work", "rfid_b200_decoder_work", "rfid_b200_mf_work",
     "rfid_b200_default_segmenter", "rfid_b200_segment_capture", "rfid_b200_ingest_capture_host",
+    "rfid_b200_tx_synth", "rfid_b200_default_sim", "rfid_b200_sim_segment_length", "rfid_b200_sim_capture",
 ]
+
+
+def default_sim(**kw):
+    p = abi.SimParams()
+    load_library().rfid_b200_default_sim(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, type(getattr(p, k))(v))
+    return p
 
 
 def default_segmenter(**kw):
@@ -199,6 +215,40 @@ class Gen2Rx:
         self._ck(rc, "rfid_b200_ingest_capture_host")
         k = n.value
         return segs[:k].copy(), recs[:k].copy(), counts[:k].copy()
+
+    # ---------------------------------------------------------------- TX synthesiser / slot simulator
+    def tx_synth(self, script, dac_rate=1000000, device="cuda:0"):
+        """script: iterable of (kind, arg) -> float32 CUDA tensor with the reader's TX envelope."""
+        import torch
+        scr = np.array([(int(k), int(a)) for k, a in script], dtype=abi.TX_COMMAND_DTYPE)
+        n = C.c_size_t(0)
+        self._ck(self.lib.rfid_b200_tx_synth(self.h, scr.ctypes.data, scr.size, dac_rate, None, 0, C.byref(n), None),
+                 "rfid_b200_tx_synth")
+        out = torch.empty(n.value, dtype=torch.float32, device=device)
+        s = torch.cuda.current_stream(out.device)
+        self._ck(self.lib.rfid_b200_tx_synth(self.h, scr.ctypes.data, scr.size, dac_rate, out.data_ptr(), out.numel(),
+                                             C.byref(n), s.cuda_stream), "rfid_b200_tx_synth")
+        return out
+
+    def sim_segment_length(self, sim):
+        n = self.lib.rfid_b200_sim_segment_length(self.h, C.byref(sim))
+        if n < 0:
+            self._ck(n, "rfid_b200_sim_segment_length")
+        return n
+
+    def sim_capture(self, sim, nseg, first_segment=0, device="cuda:0", out=None):
+        """Generate `nseg` inventory slots on the GPU.  Returns dict(iq complex64 CUDA tensor, segs CUDA uint8
+        tensor holding rfid_b200_segment[nseg], truth CUDA uint8 tensor [nseg,48] (abi.SIM_TRUTH_DTYPE))."""
+        import torch
+        seg_len = self.sim_segment_length(sim)
+        dev = torch.device(device)
+        iq = out if out is not None else torch.empty(nseg * seg_len, dtype=torch.complex64, device=dev)
+        segs = torch.zeros((nseg, 16), dtype=torch.uint8, device=dev)
+        truth = torch.zeros((nseg, 48), dtype=torch.uint8, device=dev)
+        s = torch.cuda.current_stream(dev)
+        self._ck(self.lib.rfid_b200_sim_capture(self.h, C.byref(sim), first_segment, nseg, iq.data_ptr(), segs.data_ptr(),
+                                                truth.data_ptr(), s.cuda_stream), "rfid_b200_sim_capture")
+        return {"iq": iq, "segs": segs, "truth": truth, "segment_len": seg_len}
 
     def set_window_tap(self, tensor_or_none):
         ptr = tensor_or_none.data_ptr() if tensor_or_none is not None else None

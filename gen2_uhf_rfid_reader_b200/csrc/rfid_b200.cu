@@ -17,6 +17,7 @@
 #include "rx_fused.cuh"
 #include "rx_fused_split.cuh"
 #include "rx_ingest.cuh"
+#include "tx_synth.cuh"
 
 using namespace rfid_b200;
 
@@ -57,6 +58,10 @@ struct rfid_b200_ctx {
   void* d_ing;  // level partials + totals
   void* h_stage[2]; cudaEvent_t ev_stage[2];
   std::vector<IngestBurst> h_bursts;
+  // TX synthesiser / slot simulator
+  void* d_script; size_t d_script_bytes;
+  void* d_sim_res; size_t d_sim_res_bytes;
+  void* d_sim_cnt; size_t d_sim_cnt_bytes;
 };
 
 namespace {
@@ -266,6 +271,8 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
   ctx->mf_abs0 = 0; ctx->mf_have = 0; ctx->mf_next_n = 0;
   ctx->d_mask = ctx->d_chunk = ctx->d_bursts = ctx->d_ing = nullptr;
   ctx->d_mask_bytes = ctx->d_chunk_bytes = ctx->d_bursts_bytes = 0;
+  ctx->d_script = ctx->d_sim_res = ctx->d_sim_cnt = nullptr;
+  ctx->d_script_bytes = ctx->d_sim_res_bytes = ctx->d_sim_cnt_bytes = 0;
   ctx->h_stage[0] = ctx->h_stage[1] = nullptr; ctx->ev_stage[0] = ctx->ev_stage[1] = nullptr;
   memset(&ctx->layout, 0, sizeof(ctx->layout));
   make_layout(cfg, ctx->layout);
@@ -306,7 +313,8 @@ void rfid_b200_destroy(rfid_b200_ctx* ctx)
   cudaSetDevice(ctx->device);
   drain_timing(ctx);
   void* ptrs[] = {ctx->d_win, ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
-                  ctx->d_gate, ctx->d_gate_out, ctx->d_one, ctx->d_mask, ctx->d_chunk, ctx->d_bursts, ctx->d_ing};
+                  ctx->d_gate, ctx->d_gate_out, ctx->d_one, ctx->d_mask, ctx->d_chunk, ctx->d_bursts, ctx->d_ing,
+                  ctx->d_script, ctx->d_sim_res, ctx->d_sim_cnt};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int b = 0; b < 2; b++) {
@@ -737,6 +745,181 @@ int rfid_b200_ingest_capture_host(rfid_b200_ctx* ctx, const float* h_iq, size_t 
   CK(cudaMemcpyAsync(h_results, ctx->d_res, res_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_counts, ctx->d_cnt, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return RFID_B200_OK;
+}
+
+// ------------------------------------------------------------------ TX synthesiser + slot simulator
+}  // extern "C"
+
+namespace {
+
+// waveform table sizes with the reference's arithmetic: float sample period, float quotients, truncation
+// (reader_impl.cc:51-71)
+int derive_tx_timing(int dac_rate, TxTiming& T)
+{
+  if (dac_rate <= 0) return RFID_B200_EINVAL;
+  const float sample_d = 1.0 / dac_rate * std::pow(10, 6);
+  const float n_data0 = 2 * kPW_D / sample_d, n_data1 = 4 * kPW_D / sample_d, n_pw = kPW_D / sample_d;
+  const float n_cw = kCW_D / sample_d, n_delim = kDELIM_D / sample_d, n_trcal = kTRCAL_D / sample_d;
+  const float TAG_BIT_D = (float)(1.0 / kReaderFreq * std::pow(10, 6));
+  const int RN16_D = (int)((kRN16Bits + kTagPreambleBits) * TAG_BIT_D);
+  const int EPC_D = (int)((kEPCBits + kTagPreambleBits) * TAG_BIT_D);
+  T.n_data0 = (int)n_data0; T.n_data1 = (int)n_data1; T.n_pw = (int)n_pw; T.n_delim = (int)n_delim;
+  T.n_rtcal = (int)(n_data0 + n_data1); T.n_trcal = (int)n_trcal; T.n_cw = (int)n_cw;
+  T.n_cwquery = (int)((kT1_D + kT2_D + RN16_D) / sample_d);
+  T.n_cwack = (int)((3 * kT1_D + kT2_D + EPC_D) / sample_d);
+  T.n_pdown = (int)(kP_DOWN_D / sample_d);
+  if (T.n_pw < 1 || T.n_data0 < 2) return RFID_B200_EINVAL;
+  return RFID_B200_OK;
+}
+
+// step response of the TX/RX chain measured on the recording (falling edge, raw 2 MS/s samples)
+const float kEdgeFir2Msps[] = {-0.07f, 0.32f, 0.52f, 0.155f, 0.005f, 0.03f, 0.01f, 0.01f, 0.01f, 0.005f, 0.005f};
+
+int build_sim_args(const rfid_b200_ctx* ctx, const rfid_b200_sim_params& p, SimArgs& A)
+{
+  memset(&A, 0, sizeof(A));
+  if (p.n_tags < 0 || p.n_tags > kSimMaxTags || !(p.segment_us > 0.f) || !(p.lead_us >= 0.f) || p.dac_rate <= 0) return RFID_B200_EINVAL;
+  if (ctx->cfg.adc_rate % p.dac_rate != 0) return RFID_B200_EINVAL;
+  int rc = derive_tx_timing(p.dac_rate, A.T);
+  if (rc) return rc;
+  A.p = p;
+  A.fixed_q = ctx->cfg.fixed_q;
+  A.hold = ctx->cfg.adc_rate / p.dac_rate;
+  A.sps = ctx->cfg.adc_rate / 1e6;
+  A.dac_us = 1e6 / p.dac_rate;
+  A.seg_len = (int)std::lround((double)p.segment_us * A.sps);
+  A.lead_dac = (int)std::lround((double)p.lead_us / A.dac_us);
+  // edge response stretched to the same duration at other ADC rates (linear interpolation, unit DC gain)
+  const int n2 = (int)(sizeof(kEdgeFir2Msps) / sizeof(float));
+  if (ctx->cfg.adc_rate == 2000000) {
+    A.n_fir = n2;
+    for (int i = 0; i < n2; i++) A.fir[i] = kEdgeFir2Msps[i];
+  } else {
+    int L = (int)std::lround(n2 * A.sps / 2.0);
+    if (L < 3) L = 3;
+    if (L > kSimMaxFir) L = kSimMaxFir;
+    double sum = 0.0;
+    for (int i = 0; i < L; i++) {
+      const double x = (double)i * (n2 - 1) / (L - 1);
+      const int i0 = (int)x;
+      const int i1 = i0 + 1 < n2 ? i0 + 1 : i0;
+      const double v = kEdgeFir2Msps[i0] + (kEdgeFir2Msps[i1] - kEdgeFir2Msps[i0]) * (x - i0);
+      A.fir[i] = (float)v;
+      sum += v;
+    }
+    for (int i = 0; i < L; i++) A.fir[i] = (float)(A.fir[i] / sum);
+    A.n_fir = L;
+  }
+  A.mask_words = (A.seg_len + 31) / 32 + 1;
+  if (A.seg_len < 64 || sizeof(SimShared) + 16 + (size_t)A.mask_words * 4 > 200 * 1024) return RFID_B200_EINVAL;
+  return RFID_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rfid_b200_tx_synth(rfid_b200_ctx* ctx, const rfid_b200_tx_command* h_script, int n_commands, int dac_rate, float* d_out,
+                       size_t capacity, size_t* n_samples, void* stream)
+{
+  if (!ctx || !h_script || n_commands < 0 || !n_samples) return RFID_B200_EINVAL;
+  TxTiming T;
+  int rc = derive_tx_timing(dac_rate, T);
+  if (rc) return rc;
+  std::vector<unsigned long long> off((size_t)n_commands + 1, 0ull);
+  for (int c = 0; c < n_commands; c++) {
+    if (h_script[c].kind < RFID_B200_TX_START || h_script[c].kind > RFID_B200_TX_QUERY_ADJUST) return RFID_B200_EINVAL;
+    off[c + 1] = off[c] + (unsigned long long)tx_length(T, h_script[c].kind, h_script[c].arg, ctx->cfg.fixed_q);
+  }
+  *n_samples = (size_t)off[n_commands];
+  ctx->last_launches = 0;
+  if (!d_out) return RFID_B200_OK;
+  if (capacity < *n_samples) return RFID_B200_ECAPACITY;
+  if (n_commands == 0) return RFID_B200_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t sb = (size_t)n_commands * sizeof(rfid_b200_tx_command), ob = (size_t)n_commands * 8;
+  if ((rc = grow(ctx, &ctx->d_script, &ctx->d_script_bytes, sb + ob + 16))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* d_off = reinterpret_cast<unsigned long long*>(ctx->d_script);
+  rfid_b200_tx_command* d_scr = reinterpret_cast<rfid_b200_tx_command*>(d_off + n_commands);
+  // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may go out of scope
+  CK(cudaMemcpyAsync(d_off, off.data(), ob, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_scr, h_script, sb, cudaMemcpyHostToDevice, s));
+  tx_synth_kernel<<<n_commands, 256, 0, s>>>(T, ctx->cfg.fixed_q, d_scr, d_off, n_commands, d_out);
+  CK(cudaGetLastError());
+  ctx->last_launches = 1;
+  return RFID_B200_OK;
+}
+
+void rfid_b200_default_sim(rfid_b200_sim_params* p)
+{
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->seed = 1234;
+  p->n_tags = 1;
+  p->closed_loop = 1;
+  p->dac_rate = 1000000;  // apps/reader.py:56
+  p->segment_us = 8480.f;
+  p->lead_us = 400.f;
+  p->noise_sigma = 0.0030f;
+  p->tag_gain = 0.0227f;
+  p->tag_phase = std::atan2(0.192f, -0.981f);
+  p->clock_pct = 0.8f;
+  p->leak_re = 0.2846f;
+  p->leak_im = -0.0349f;
+  p->floor_level = 0.004f;
+}
+
+int rfid_b200_sim_segment_length(const rfid_b200_ctx* ctx, const rfid_b200_sim_params* p)
+{
+  if (!ctx || !p) return RFID_B200_EINVAL;
+  SimArgs A;
+  int rc = build_sim_args(ctx, *p, A);
+  return rc ? rc : A.seg_len;
+}
+
+int rfid_b200_sim_capture(rfid_b200_ctx* ctx, const rfid_b200_sim_params* p, int64_t first_segment, int nseg, float* d_iq,
+                          rfid_b200_segment* d_segs, rfid_b200_sim_truth* d_truth, void* stream)
+{
+  if (!ctx || !p || !d_iq || !d_segs || nseg < 0 || first_segment < 0) return RFID_B200_EINVAL;
+  SimArgs A;
+  int rc = build_sim_args(ctx, *p, A);
+  if (rc) return rc;
+  ctx->last_launches = 0;
+  if (nseg == 0) return RFID_B200_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = ((sizeof(SimShared) + 15) & ~(size_t)15) + (size_t)A.mask_words * 4;
+  CK(cudaFuncSetAttribute((const void*)sim_slot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  A.first_segment = first_segment; A.nseg = nseg;
+  A.iq = reinterpret_cast<float2*>(d_iq); A.segs = d_segs; A.truth = d_truth;
+  int launches = 0;
+  if (!p->closed_loop) {
+    A.phase = 2;
+    sim_slot_kernel<<<nseg, kSimThreads, smem, s>>>(A);
+    CK(cudaGetLastError());
+    launches = 1;
+  } else {
+    // Query + RN16 replies -> decode the RN16 window with this context's receive chain -> ACK(decoded) + EPC
+    if (!pick_kernel(ctx->cfg)) { ctx->last_error = "capture mode supports decim = 5 only in this build"; return RFID_B200_EINVAL; }
+    if ((rc = grow(ctx, &ctx->d_sim_res, &ctx->d_sim_res_bytes, (size_t)nseg * sizeof(rfid_b200_window_result)))) return rc;
+    if ((rc = grow(ctx, &ctx->d_sim_cnt, &ctx->d_sim_cnt_bytes, (size_t)nseg * 4))) return rc;
+    A.phase = 0;
+    sim_slot_kernel<<<nseg, kSimThreads, smem, s>>>(A);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->d_sim_res, 0, (size_t)nseg * sizeof(rfid_b200_window_result), s));
+    rc = rfid_b200_decode_capture(ctx, d_iq, (size_t)nseg * A.seg_len, d_segs, nseg, 1, (rfid_b200_window_result*)ctx->d_sim_res,
+                                  (int32_t*)ctx->d_sim_cnt, s);
+    if (rc) return rc;
+    A.phase = 1;
+    A.rn16_records = (const rfid_b200_window_result*)ctx->d_sim_res;
+    A.rn16_counts = (const int32_t*)ctx->d_sim_cnt;
+    sim_slot_kernel<<<nseg, kSimThreads, smem, s>>>(A);
+    CK(cudaGetLastError());
+    launches = 3;
+  }
+  ctx->last_launches = launches;
   return RFID_B200_OK;
 }
 

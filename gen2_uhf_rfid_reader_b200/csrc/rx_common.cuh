@@ -25,6 +25,7 @@ namespace rfid_b200 {
 // ---- protocol constants: include/rfid/global_vars.h:72-143 of the reference ----
 constexpr int kT1_D = 240;                // us
 constexpr int kPW_D = 12;                 // us
+constexpr int kT2_D = 480, kCW_D = 250, kP_DOWN_D = 2000, kDELIM_D = 12, kTRCAL_D = 200;  // us, reader TX (global_vars.h:88-97)
 constexpr int kNumPulsesCommand = 5;
 constexpr int kTagPreambleBits = 6;
 constexpr int kRN16Bits = 17;

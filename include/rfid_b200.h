@@ -207,6 +207,76 @@ RFID_B200_API int rfid_b200_ingest_capture_host(rfid_b200_ctx* ctx, const float*
                                                 rfid_b200_segment* h_segs, int seg_capacity, int* nseg,
                                                 rfid_b200_window_result* h_results, int32_t* h_counts);
 
+/* ---------------- reader TX synthesiser + closed-loop slot simulator ----------------
+ * The reader block's PIE command waveforms (reader_impl.cc:51-125 tables, :237-372 what every
+ * Gen2-logic state emits, :383-443 CRC-5) generated on the GPU, sample for sample identical to
+ * what reader_impl::general_work writes to its output port (float 0.0/1.0 at the DAC rate). */
+enum {
+  RFID_B200_TX_START = 0,        /* START: carrier before the first Query          (reader_impl.cc:237-243) */
+  RFID_B200_TX_QUERY = 1,        /* SEND_QUERY: preamble + Query + carrier         (:265-285) */
+  RFID_B200_TX_QUERY_REP = 2,    /* SEND_QUERY_REP                                 (:330-344) */
+  RFID_B200_TX_ACK = 3,          /* SEND_ACK: frame-sync + 01 + RN16 (arg)         (:290-320) */
+  RFID_B200_TX_CW = 4,           /* SEND_CW: carrier during the EPC reply          (:322-328) */
+  RFID_B200_TX_NAK = 5,          /* SEND_NAK_Q / SEND_NAK_QR                       (:245-263) */
+  RFID_B200_TX_POWER_DOWN = 6,   /* POWER_DOWN                                     (:228-235) */
+  RFID_B200_TX_QUERY_ADJUST = 7  /* SEND_QUERY_ADJUST                              (:346-366) */
+};
+typedef struct rfid_b200_tx_command {
+  int32_t kind; /* RFID_B200_TX_* */
+  int32_t arg;  /* ACK: the 16-bit RN16 to echo */
+} rfid_b200_tx_command;
+
+/* Waveform of a script of emissions, written to d_out (device, `capacity` floats).  *n_samples
+ * receives the total length (also on RFID_B200_ECAPACITY); d_out may be NULL to query it. */
+RFID_B200_API int rfid_b200_tx_synth(rfid_b200_ctx* ctx, const rfid_b200_tx_command* h_script, int n_commands,
+                                     int dac_rate, float* d_out, size_t capacity, size_t* n_samples, void* stream);
+
+/* Inventory-slot simulator: one segment = one slot = carrier, Query (slot 0 of a round) or QueryRep,
+ * RN16 replies of the tags that picked this slot, ACK, EPC reply, carrier.  Signal model (SURVEY.md 8d,
+ * calibrated on misc/data/file_source_test): rx = (L + sum_k g_k b_k[n]) * env[n] + w[n], env = the
+ * reader waveform above held to the ADC rate and shaped by the measured TX/RX edge response, b_k = FM0
+ * half-symbol levels (TAG_PREAMBLE, data, dummy 1) at BLF 40 kHz starting T1 after the command.
+ * closed_loop != 0: the first part of every slot is generated and decoded by this context's receive
+ * chain, the ACK echoes the RN16 that was decoded, and only a tag whose RN16 matches sends its EPC
+ * (collided or empty slots therefore end in silence, as with a real reader); closed_loop == 0: the ACK
+ * echoes the strongest tag's RN16.  All randomness is counter-based: segment i of the global numbering is
+ * the same whichever rank generates it. */
+typedef struct rfid_b200_sim_params {
+  uint64_t seed;
+  int32_t n_tags;      /* tags in the field (0..16); each draws a slot per inventory round */
+  int32_t closed_loop;
+  int32_t dac_rate;    /* reader TX rate (apps/reader.py:56 -> 1000000); adc_rate must be a multiple */
+  float segment_us;    /* slot length (8480 = the recording's round period) */
+  float lead_us;       /* carrier before the first command (400) */
+  float noise_sigma;   /* per component (0.0030) */
+  float tag_gain;      /* |g| (0.0227) */
+  float tag_phase;     /* arg g, rad */
+  float clock_pct;     /* tag clock tolerance, percent (0.8) */
+  float leak_re, leak_im; /* carrier leakage (0.2846, -0.0349) */
+  float floor_level;   /* envelope inside a low pulse (0.004) */
+  int32_t reserved[2];
+} rfid_b200_sim_params;
+
+typedef struct rfid_b200_sim_truth {
+  int32_t is_query;       /* 1: the slot starts with a Query, 0: QueryRep */
+  int32_t n_replies;      /* tags that answered with an RN16 */
+  int32_t strongest_rn16; /* RN16 of the strongest of them, -1: empty slot */
+  int32_t acked_rn16;     /* RN16 in the ACK (closed loop: what the receive chain decoded), -1: no ACK sent */
+  int32_t replier;        /* tag that sent its EPC, -1: none */
+  int32_t reserved[3];
+  uint8_t epc[16];        /* PC + EPC + CRC-16 it sent (zeros if none) */
+} rfid_b200_sim_truth;
+
+RFID_B200_API void rfid_b200_default_sim(rfid_b200_sim_params* p);
+/* raw samples per segment for these settings (negative: error) */
+RFID_B200_API int rfid_b200_sim_segment_length(const rfid_b200_ctx* ctx, const rfid_b200_sim_params* p);
+/* Generate segments [first_segment, first_segment + nseg) into d_iq (device, nseg * segment_length
+ * complex64), with their segment table (device, offsets relative to d_iq) and ground truth (device, may
+ * be NULL).  Asynchronous on `stream` except for buffer growth. */
+RFID_B200_API int rfid_b200_sim_capture(rfid_b200_ctx* ctx, const rfid_b200_sim_params* p, int64_t first_segment,
+                                        int nseg, float* d_iq, rfid_b200_segment* d_segs,
+                                        rfid_b200_sim_truth* d_truth, void* stream);
+
 /* ---------------- block mode (GNU Radio drop-in) ----------------
  * Called from the thin host blocks' general_work(); HOST pointers, owned by the
  * scheduler, touched only during the call.  State lives in the context (device

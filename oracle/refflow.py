@@ -92,7 +92,7 @@ class FlowLib:
     def reader_script(self, rn16_bits, dac_rate=1000000):
         """scripted run of the reader block alone (CPU only): returns (tx envelope, n_queries_sent)"""
         bits = np.ascontiguousarray(rn16_bits, dtype=np.float32).reshape(-1, 16)
-        tx = np.zeros(bits.shape[0] * 12000 + 8000, dtype=np.float32)
+        tx = np.zeros((bits.shape[0] * 12000 + 8000) * max(1, -(-dac_rate // 1000000)), dtype=np.float32)
         n = C.c_size_t(0)
         nq = self.lib.gen2flow_reader_script(bits.ctypes.data_as(C.POINTER(C.c_float)), bits.shape[0], dac_rate,
                                              tx.ctypes.data_as(C.POINTER(C.c_float)), tx.size, C.byref(n))
