@@ -20,7 +20,18 @@
 namespace rfid_b200 {
 
 constexpr int kS = 5;                         // tile stages
-constexpr int kSplitThreads = 32 * 5;
+#ifndef RFID_B200_SPLIT_WORKER_WARPS
+#define RFID_B200_SPLIT_WORKER_WARPS 1
+#endif
+constexpr int kSWWarps = RFID_B200_SPLIT_WORKER_WARPS;   // worker warps of the split kernel
+constexpr int kSWThreads = kSWWarps * 32;
+constexpr int kSplitWarps = 3 + kSWWarps;     // chain, control, workers, decoder
+constexpr int kSplitThreads = 32 * kSplitWarps;
+__device__ __forceinline__ void split_sync_workers()
+{
+  if (kSWWarps == 1) __syncwarp();
+  else bar_sync_workers();
+}
 constexpr int kRing = kS * kTT;               // time-indexed ring length (samples)
 
 struct SplitShared {
@@ -207,7 +218,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
 #endif
   // roles rotate over the hardware warps so that the chain warps of co-resident CTAs spread over the SM
   // sub-partitions: 0 chain, 1 control, 2..3 workers, 4 decoder
-  const int role = ((threadIdx.x >> 5) + blockIdx.x) % 5;
+  const int role = ((threadIdx.x >> 5) + blockIdx.x) % kSplitWarps;
   const RxConfig& C = A.cfg;
   const rfid_b200_segment sg = A.segs[seg];
   const int n_out = (int)(sg.length / DECIM);
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; s++) mbar_init(&B.raw_full[s], 1);
     for (int s = 0; s < kS; s++) {
-      mbar_init(&B.tile_full[s], kWorkerWarps);
+      mbar_init(&B.tile_full[s], kSWWarps);
       mbar_init(&B.chain_done[s], 1);
       mbar_init(&B.elist_ready[s], 1);
       mbar_init(&B.tile_free[s], 2);  // control (done with the stage's lookbacks) + chain (window emission done)
@@ -241,37 +252,64 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
   }
   __syncthreads();
 
-  if (role == 2 || role == 3) {
+  if (role >= 2 && role < 2 + kSWWarps) {
     // =========================================================== workers
     const int wt = (role - 2) * 32 + lane;
+    // raw tile geometry.  Tile k >= 1 starts at raw sample D*kTT*k - (D-1) of the segment, moved down to an even
+    // absolute index (16-byte TMA source); tile 0 starts at the segment's first (even-aligned) sample.  Interior
+    // tiles are all alike: `fast_tiles` of them can be issued with a constant byte count and a pointer bump.
+    const int odd = (int)(sg.offset & 1ull);
+    const uint32_t fast_bytes = (uint32_t)((DECIM * kTT + 2 * odd) * 8);
+    int fast_tiles = 0;  // tiles 1 .. fast_tiles-1 take the fast path
+    {
+      // tile k is "interior" when its last sample D*(k*kTT + kTT-1) exists and the rounded-up copy stays inside the capture
+      const long long by_len = ((long long)sg.length - 1 - (long long)DECIM * (kTT - 1)) / ((long long)DECIM * kTT);
+      const long long room = (long long)A.n_raw - (long long)sg.offset + (DECIM - 1) + odd - (DECIM * kTT + 2 * odd);
+      const long long by_buf = room >= 0 ? room / ((long long)DECIM * kTT) : -1;
+      long long f = (by_len < by_buf ? by_len : by_buf) + 1;
+      if (sg.length < (unsigned)(DECIM * kTT)) f = 0;
+      fast_tiles = f < 0 ? 0 : (f > ntiles ? ntiles : (int)f);
+    }
+    const float2* const fast_src = A.iq + sg.offset - (DECIM - 1) - odd;  // + D*kTT*k for tile k >= 1
+    auto load_tile = [&](int k, int rs_) {
+      float2* dst = raw + (size_t)rs_ * A.raw_stage_samples;
+      if (k >= 1 && k < fast_tiles) {
+        mbar_arrive_expect_tx(&B.raw_full[rs_], fast_bytes);
+        tma_load_1d(dst, fast_src + (size_t)k * (DECIM * kTT), fast_bytes, &B.raw_full[rs_]);
+      } else {
+        issue_tile_load<DECIM>(A, sg, k, dst, &B.raw_full[rs_]);
+      }
+    };
     if (wt == 0) {
-      for (int k = 0; k < kRawStages && k < ntiles; k++)
-        issue_tile_load<DECIM>(A, sg, k, raw + (size_t)k * A.raw_stage_samples, &B.raw_full[k]);
+      for (int k = 0; k < kRawStages && k < ntiles; k++) load_tile(k, k);
     }
     const int bmask = A.bhist_size - 1;
     const float winlen_f = (float)C.win_length, dclen_f = (float)C.dc_length;
     float2 b_keep = make_float2(0.f, 0.f);
     PH_DECL
+    int rs = 0, ts = 0;                  // k % kRawStages, k % kS
+    uint32_t raw_par = 0, free_par = 1;  // (k / kRawStages) & 1, ((k / kS) & 1) ^ 1
     for (int k = 0; k < ntiles; k++) {
-      const int rs = k % kRawStages, ts = k % kS;
       const float2* stage = raw + (size_t)rs * A.raw_stage_samples;
-      const int delta = (int)(tile_load_start<DECIM>(sg.offset, k) - (long long)DECIM * k * kTT);
+      const int delta = -odd - (k > 0 ? DECIM - 1 : 0);  // tile_load_start(k) - D*kTT*k
       const int nvalid = min(kTT, n_out - k * kTT);
       PH_MARK(0)
-      mbar_wait(&B.raw_full[rs], (k / kRawStages) & 1);
+      mbar_wait(&B.raw_full[rs], raw_par);
       PH_MARK(1)
       // ---- block sums B(n) = x[D*n-D+1 .. D*n], ascending
 #pragma unroll
-      for (int r = 0; r < kTT / kWorkerThreads; r++) {
-        const int t = wt + r * kWorkerThreads;
+      for (int r = 0; r < kTT / kSWThreads; r++) {
+        const int t = wt + r * kSWThreads;
         if (t < nvalid) {
           const int n = k * kTT + t;
           const int base = DECIM * t - (DECIM - 1) - delta;
           float2 x[DECIM];
+          if (k == 0 && t == 0) {  // the segment's very first block reaches before sample 0: those read as +0
 #pragma unroll
-          for (int j = 0; j < DECIM; j++) {
-            const bool before = (k == 0) && (DECIM * t - (DECIM - 1) + j < 0);  // before sample 0: +0
-            x[j] = before ? make_float2(0.f, 0.f) : stage[base + j];
+            for (int j = 0; j < DECIM; j++) x[j] = j < DECIM - 1 ? make_float2(0.f, 0.f) : stage[base + j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < DECIM; j++) x[j] = stage[base + j];
           }
           float2 b = x[0];
 #pragma unroll
@@ -297,17 +335,16 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         }
       }
       PH_MARK(2)
-      bar_sync_workers();  // raw stage consumed, block sums visible
-      if (wt == 0 && k + kRawStages < ntiles)
-        issue_tile_load<DECIM>(A, sg, k + kRawStages, raw + (size_t)rs * A.raw_stage_samples, &B.raw_full[rs]);
+      split_sync_workers();  // raw stage consumed, block sums visible
+      if (wt == 0 && k + kRawStages < ntiles) load_tile(k + kRawStages, rs);
       PH_MARK(3)
-      mbar_wait_lazy(&B.tile_free[ts], ((k / kS) & 1) ^ 1);  // control is done with tile k - 5
+      mbar_wait_lazy(&B.tile_free[ts], free_par);  // control is done with tile k - 5
       PH_MARK(4)
-      float a_reg[kTT / kWorkerThreads];
-      float2 y_reg[kTT / kWorkerThreads];
+      float a_reg[kTT / kSWThreads];
+      float2 y_reg[kTT / kSWThreads];
 #pragma unroll
-      for (int r = 0; r < kTT / kWorkerThreads; r++) {
-        const int t = wt + r * kWorkerThreads;
+      for (int r = 0; r < kTT / kSWThreads; r++) {
+        const int t = wt + r * kSWThreads;
         a_reg[r] = 0.f;
         y_reg[r] = make_float2(0.f, 0.f);
         if (t < nvalid) {
@@ -336,20 +373,20 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         }
       }
       PH_MARK(5)
-      bar_sync_workers();  // this tile's |y| and y visible to both workers; every block sum has been consumed
+      split_sync_workers();  // this tile's |y| and y visible to both workers; every block sum has been consumed
       PH_MARK(6)
       if (MFQ > 0) {
-        const int t_hi = wt + kWorkerThreads * (kTT / kWorkerThreads - 1);  // this thread's last output of the tile
+        const int t_hi = wt + kSWThreads * (kTT / kSWThreads - 1);  // this thread's last output of the tile
         if (t_hi >= kTT - (MFQ - 1) && t_hi < nvalid) bhist[t_hi - (kTT - (MFQ - 1))] = b_keep;
       }
       {
         // ring differences of this thread's samples, all divisions in flight together (gate_impl.cc:131,141); the
         // multiply-correct quotients are used when every input of the warp is inside the verified range
-        float xd[kTT / kWorkerThreads], xr[kTT / kWorkerThreads], xi[kTT / kWorkerThreads];
+        float xd[kTT / kSWThreads], xr[kTT / kSWThreads], xi[kTT / kSWThreads];
         bool all_ok = C.win_div_fast && C.dc_div_fast;
 #pragma unroll
-        for (int r = 0; r < kTT / kWorkerThreads; r++) {
-          const int t = wt + r * kWorkerThreads;
+        for (int r = 0; r < kTT / kSWThreads; r++) {
+          const int t = wt + r * kSWThreads;
           xd[r] = xr[r] = xi[r] = 1.0f;
           if (t < nvalid) {
             int ia = ts * kTT + t - C.win_length;
@@ -365,8 +402,8 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         }
         if (__all_sync(0xffffffffu, all_ok)) {
 #pragma unroll
-          for (int r = 0; r < kTT / kWorkerThreads; r++) {
-            const int t = wt + r * kWorkerThreads;
+          for (int r = 0; r < kTT / kSWThreads; r++) {
+            const int t = wt + r * kSWThreads;
             if (t < nvalid) {
               ring_d[ts * kTT + t] = f_div_fast(xd[r], winlen_f, C.win_recip);
               etile[(ts * 2 + 0) * kTT + t] = f_div_fast(xr[r], dclen_f, C.dc_recip);
@@ -375,8 +412,8 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
           }
         } else {  // an exact zero, a denormal, or an unverified divisor somewhere in the warp: IEEE division
 #pragma unroll
-          for (int r = 0; r < kTT / kWorkerThreads; r++) {
-            const int t = wt + r * kWorkerThreads;
+          for (int r = 0; r < kTT / kSWThreads; r++) {
+            const int t = wt + r * kSWThreads;
             if (t < nvalid) {
               ring_d[ts * kTT + t] = f_div_const(xd[r], winlen_f, C.win_recip, C.win_div_fast);
               etile[(ts * 2 + 0) * kTT + t] = f_div_const(xr[r], dclen_f, C.dc_recip, C.dc_div_fast);
@@ -388,6 +425,8 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.tile_full[ts]);
       PH_MARK(7)
+      if (++rs == kRawStages) { rs = 0; raw_par ^= 1u; }
+      if (++ts == kS) { ts = 0; free_par ^= 1u; }
     }
     if (wt == 0) { PH_DUMP(8) }
     if (wt == 0) { PH_END(21) }
