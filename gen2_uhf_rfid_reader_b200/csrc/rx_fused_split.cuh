@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
     }
     const int bmask = A.bhist_size - 1;
     const float winlen_f = (float)C.win_length, dclen_f = (float)C.dc_length;
-    float2 b_keep = make_float2(0.f, 0.f);
+    float2 b_keep[MFQ > 1 ? MFQ - 1 : 1];
+#pragma unroll
+    for (int m = 0; m < (MFQ > 1 ? MFQ - 1 : 1); m++) b_keep[m] = make_float2(0.f, 0.f);
     PH_DECL
     int rs = 0, ts = 0;                  // k % kRawStages, k % kS
     uint32_t raw_par = 0, free_par = 1;  // (k / kRawStages) & 1, ((k / kS) & 1) ^ 1
@@ -296,128 +298,255 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       PH_MARK(0)
       mbar_wait(&B.raw_full[rs], raw_par);
       PH_MARK(1)
-      // ---- block sums B(n) = x[D*n-D+1 .. D*n], ascending
+      if constexpr (MFQ > 0 && kSWWarps == 1) {
+        // ---- consecutive mapping: this lane owns outputs t0 .. t0+3 of the tile; block sums travel between lanes by
+        // shuffle and between tiles in registers, wide shared-memory accesses throughout
+        constexpr int Q = kTT / 32;
+        static_assert(MFQ - 1 <= Q, "block-sum halo comes from the neighbouring lane only");
+        const int t0 = Q * lane;
+        const int base = DECIM * t0 - (DECIM - 1) - delta;  // stage index of x[D*t0 - (D-1)]; parity = odd
+        // block sums B(n) = x[D*n-D+1 .. D*n], ascending; two outputs' worth of raw samples in registers at a time
+        float2 w[MFQ - 1 + Q];
+        static_assert(Q % 2 == 0 && (2 * DECIM) % 2 == 0, "");
 #pragma unroll
-      for (int r = 0; r < kTT / kSWThreads; r++) {
-        const int t = wt + r * kSWThreads;
-        if (t < nvalid) {
-          const int n = k * kTT + t;
-          const int base = DECIM * t - (DECIM - 1) - delta;
-          float2 x[DECIM];
-          if (k == 0 && t == 0) {  // the segment's very first block reaches before sample 0: those read as +0
-#pragma unroll
-            for (int j = 0; j < DECIM; j++) x[j] = j < DECIM - 1 ? make_float2(0.f, 0.f) : stage[base + j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < DECIM; j++) x[j] = stage[base + j];
-          }
-          float2 b = x[0];
-#pragma unroll
-          for (int j = 1; j < DECIM; j++) b = c_add2(b, x[j]);
-          if (MFQ > 0) {
-            bhist[MFQ - 1 + t] = b;               // bhist[0 .. MFQ-2] = the last MFQ-1 block sums of the previous tile
-            if (t >= kTT - (MFQ - 1)) b_keep = b;  // ... which these threads hand over after the tile
-          } else {
-            bhist[n & bmask] = b;
-          }
-          if (MFQ == 0 && C.mf_rem) {
-            float2 p = make_float2(0.f, 0.f);
-            bool started = false;
+        for (int h = 0; h < Q; h += 2) {
+          float2 x[2 * DECIM];
+          if (odd == 0 && k > 0) {
+            const float4* p4 = reinterpret_cast<const float4*>(stage + base + DECIM * h);
 #pragma unroll
             for (int j = 0; j < DECIM; j++) {
-              if (j >= DECIM - C.mf_rem) {
-                p = started ? c_add(p, x[j]) : x[j];
-                started = true;
-              }
+              const float4 v = p4[j];
+              x[2 * j] = make_float2(v.x, v.y);
+              x[2 * j + 1] = make_float2(v.z, v.w);
             }
-            phist[n & bmask] = p;
-          }
-        }
-      }
-      PH_MARK(2)
-      split_sync_workers();  // raw stage consumed, block sums visible
-      if (wt == 0 && k + kRawStages < ntiles) load_tile(k + kRawStages, rs);
-      PH_MARK(3)
-      mbar_wait_lazy(&B.tile_free[ts], free_par);  // control is done with tile k - 5
-      PH_MARK(4)
-      float a_reg[kTT / kSWThreads];
-      float2 y_reg[kTT / kSWThreads];
-#pragma unroll
-      for (int r = 0; r < kTT / kSWThreads; r++) {
-        const int t = wt + r * kSWThreads;
-        a_reg[r] = 0.f;
-        y_reg[r] = make_float2(0.f, 0.f);
-        if (t < nvalid) {
-          const int n = k * kTT + t;
-          float2 y;
-          if (MFQ > 0) {
-            const float2* bp = bhist + t;  // B(n-MFQ+1) .. B(n) are bp[0 .. MFQ-1]
-            y = bp[0];
-#pragma unroll
-            for (int m = 1; m < MFQ; m++) y = c_add2(y, bp[m]);
           } else {
-            int m = n - C.mf_q + 1;
-            if (C.mf_rem) {
-              y = phist[(n - C.mf_q) & bmask];
-            } else {
-              y = bhist[m & bmask];
-              m++;
+#pragma unroll
+            for (int j = 0; j < 2 * DECIM; j++) {
+              const bool before = (k == 0) && (DECIM * (t0 + h) - (DECIM - 1) + j < 0);  // before sample 0 of the segment: +0
+              x[j] = before ? make_float2(0.f, 0.f) : stage[base + DECIM * h + j];
             }
-            for (; m <= n; m++) y = c_add(y, bhist[m & bmask]);
           }
-          const float a = cabsf_ref(y.x, y.y);  // gate_impl.cc:130
-          ring_y[ts * kTT + t] = y;
-          ring_a[ts * kTT + t] = a;
-          a_reg[r] = a;
-          y_reg[r] = y;
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            float2 b = x[DECIM * q];
+#pragma unroll
+            for (int j = 1; j < DECIM; j++) b = c_add2(b, x[DECIM * q + j]);
+            w[MFQ - 1 + h + q] = b;
+          }
         }
-      }
-      PH_MARK(5)
-      split_sync_workers();  // this tile's |y| and y visible to both workers; every block sum has been consumed
-      PH_MARK(6)
-      if (MFQ > 0) {
-        const int t_hi = wt + kSWThreads * (kTT / kSWThreads - 1);  // this thread's last output of the tile
-        if (t_hi >= kTT - (MFQ - 1) && t_hi < nvalid) bhist[t_hi - (kTT - (MFQ - 1))] = b_keep;
-      }
-      {
-        // ring differences of this thread's samples, all divisions in flight together (gate_impl.cc:131,141); the
-        // multiply-correct quotients are used when every input of the warp is inside the verified range
-        float xd[kTT / kSWThreads], xr[kTT / kSWThreads], xi[kTT / kSWThreads];
+        __syncwarp();  // raw stage consumed
+        if (lane == 0 && k + kRawStages < ntiles) load_tile(k + kRawStages, rs);
+        PH_MARK(2)
+#pragma unroll
+        for (int m = 0; m < MFQ - 1; m++) {  // B(n-MFQ+1 ..) of the first outputs: the previous lane's / tile's last block sums
+          const float2 mine = w[Q + m];
+          const float ux = __shfl_up_sync(0xffffffffu, mine.x, 1), uy = __shfl_up_sync(0xffffffffu, mine.y, 1);
+          w[m] = lane ? make_float2(ux, uy) : b_keep[m];
+          b_keep[m] = make_float2(__shfl_sync(0xffffffffu, mine.x, 31), __shfl_sync(0xffffffffu, mine.y, 31));
+        }
+        PH_MARK(3)
+        mbar_wait_lazy(&B.tile_free[ts], free_par);  // control is done with tile k - 5
+        PH_MARK(4)
+        float2 y[Q];
+        float a[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          y[q] = w[q];
+#pragma unroll
+          for (int m = 1; m < MFQ; m++) y[q] = c_add2(y[q], w[q + m]);
+          a[q] = cabsf_ref(y[q].x, y[q].y);  // gate_impl.cc:130
+        }
+        {
+          float4* py = reinterpret_cast<float4*>(ring_y + ts * kTT + t0);
+#pragma unroll
+          for (int q = 0; q < Q; q += 2) py[q / 2] = make_float4(y[q].x, y[q].y, y[q + 1].x, y[q + 1].y);
+          float4* pa = reinterpret_cast<float4*>(ring_a + ts * kTT + t0);
+#pragma unroll
+          for (int q = 0; q < Q; q += 4) pa[q / 4] = make_float4(a[q], a[q + 1], a[q + 2], a[q + 3]);
+        }
+        PH_MARK(5)
+        __syncwarp();  // this tile's |y| and y visible to the lookbacks below
+        PH_MARK(6)
+        // ring differences (gate_impl.cc:131,141), all divisions in flight together; the multiply-correct quotients
+        // are used when every input of the warp is inside the verified range
+        float xd[Q], xr[Q], xi[Q];
+        int ia = ts * kTT + t0 - C.win_length, iy = ts * kTT + t0 - C.dc_length;
+        if (ia < 0) ia += kRing;
+        if (iy < 0) iy += kRing;
+        if (((C.win_length | C.dc_length) & 3) == 0) {  // lookback groups are aligned and never straddle the ring's end
+#pragma unroll
+          for (int q = 0; q < Q; q += 4) {
+            const float4 oa = *reinterpret_cast<const float4*>(ring_a + ia + q);
+            xd[q] = f_sub(a[q], oa.x); xd[q + 1] = f_sub(a[q + 1], oa.y);
+            xd[q + 2] = f_sub(a[q + 2], oa.z); xd[q + 3] = f_sub(a[q + 3], oa.w);
+          }
+#pragma unroll
+          for (int q = 0; q < Q; q += 2) {
+            const float4 oy = *reinterpret_cast<const float4*>(ring_y + iy + q);
+            xr[q] = f_sub(y[q].x, oy.x); xi[q] = f_sub(y[q].y, oy.y);
+            xr[q + 1] = f_sub(y[q + 1].x, oy.z); xi[q + 1] = f_sub(y[q + 1].y, oy.w);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < Q; q++) {
+            int ja = ia + q, jy = iy + q;
+            if (ja >= kRing) ja -= kRing;
+            if (jy >= kRing) jy -= kRing;
+            const float2 old = ring_y[jy];
+            xd[q] = f_sub(a[q], ring_a[ja]);
+            xr[q] = f_sub(y[q].x, old.x);
+            xi[q] = f_sub(y[q].y, old.y);
+          }
+        }
         bool all_ok = C.win_div_fast && C.dc_div_fast;
 #pragma unroll
-        for (int r = 0; r < kTT / kSWThreads; r++) {
-          const int t = wt + r * kSWThreads;
-          xd[r] = xr[r] = xi[r] = 1.0f;
-          if (t < nvalid) {
-            int ia = ts * kTT + t - C.win_length;
-            if (ia < 0) ia += kRing;
-            int iy = ts * kTT + t - C.dc_length;
-            if (iy < 0) iy += kRing;
-            const float2 old = ring_y[iy];
-            xd[r] = f_sub(a_reg[r], ring_a[ia]);
-            xr[r] = f_sub(y_reg[r].x, old.x);
-            xi[r] = f_sub(y_reg[r].y, old.y);
-          }
-          all_ok = all_ok && f_div_fast_ok(xd[r]) && f_div_fast_ok(xr[r]) && f_div_fast_ok(xi[r]);
-        }
+        for (int q = 0; q < Q; q++) all_ok = all_ok && f_div_fast_ok(xd[q]) && f_div_fast_ok(xr[q]) && f_div_fast_ok(xi[q]);
+        float qd[Q], qr[Q], qi[Q];
         if (__all_sync(0xffffffffu, all_ok)) {
 #pragma unroll
-          for (int r = 0; r < kTT / kSWThreads; r++) {
-            const int t = wt + r * kSWThreads;
-            if (t < nvalid) {
-              ring_d[ts * kTT + t] = f_div_fast(xd[r], winlen_f, C.win_recip);
-              etile[(ts * 2 + 0) * kTT + t] = f_div_fast(xr[r], dclen_f, C.dc_recip);
-              etile[(ts * 2 + 1) * kTT + t] = f_div_fast(xi[r], dclen_f, C.dc_recip);
-            }
+          for (int q = 0; q < Q; q++) {
+            qd[q] = f_div_fast(xd[q], winlen_f, C.win_recip);
+            qr[q] = f_div_fast(xr[q], dclen_f, C.dc_recip);
+            qi[q] = f_div_fast(xi[q], dclen_f, C.dc_recip);
           }
         } else {  // an exact zero, a denormal, or an unverified divisor somewhere in the warp: IEEE division
 #pragma unroll
+          for (int q = 0; q < Q; q++) {
+            qd[q] = f_div_const(xd[q], winlen_f, C.win_recip, C.win_div_fast);
+            qr[q] = f_div_const(xr[q], dclen_f, C.dc_recip, C.dc_div_fast);
+            qi[q] = f_div_const(xi[q], dclen_f, C.dc_recip, C.dc_div_fast);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q += 4) {
+          *reinterpret_cast<float4*>(ring_d + ts * kTT + t0 + q) = make_float4(qd[q], qd[q + 1], qd[q + 2], qd[q + 3]);
+          *reinterpret_cast<float4*>(etile + (ts * 2 + 0) * kTT + t0 + q) = make_float4(qr[q], qr[q + 1], qr[q + 2], qr[q + 3]);
+          *reinterpret_cast<float4*>(etile + (ts * 2 + 1) * kTT + t0 + q) = make_float4(qi[q], qi[q + 1], qi[q + 2], qi[q + 3]);
+        }
+      } else {
+        // ---- block sums B(n) = x[D*n-D+1 .. D*n], ascending
+  #pragma unroll
+        for (int r = 0; r < kTT / kSWThreads; r++) {
+          const int t = wt + r * kSWThreads;
+          if (t < nvalid) {
+            const int n = k * kTT + t;
+            const int base = DECIM * t - (DECIM - 1) - delta;
+            float2 x[DECIM];
+            if (k == 0 && t == 0) {  // the segment's very first block reaches before sample 0: those read as +0
+  #pragma unroll
+              for (int j = 0; j < DECIM; j++) x[j] = j < DECIM - 1 ? make_float2(0.f, 0.f) : stage[base + j];
+            } else {
+  #pragma unroll
+              for (int j = 0; j < DECIM; j++) x[j] = stage[base + j];
+            }
+            float2 b = x[0];
+  #pragma unroll
+            for (int j = 1; j < DECIM; j++) b = c_add2(b, x[j]);
+            if (MFQ > 0) {
+              bhist[MFQ - 1 + t] = b;               // bhist[0 .. MFQ-2] = the last MFQ-1 block sums of the previous tile
+              if (t >= kTT - (MFQ - 1)) b_keep[0] = b;  // ... which these threads hand over after the tile
+            } else {
+              bhist[n & bmask] = b;
+            }
+            if (MFQ == 0 && C.mf_rem) {
+              float2 p = make_float2(0.f, 0.f);
+              bool started = false;
+  #pragma unroll
+              for (int j = 0; j < DECIM; j++) {
+                if (j >= DECIM - C.mf_rem) {
+                  p = started ? c_add(p, x[j]) : x[j];
+                  started = true;
+                }
+              }
+              phist[n & bmask] = p;
+            }
+          }
+        }
+        PH_MARK(2)
+        split_sync_workers();  // raw stage consumed, block sums visible
+        if (wt == 0 && k + kRawStages < ntiles) load_tile(k + kRawStages, rs);
+        PH_MARK(3)
+        mbar_wait_lazy(&B.tile_free[ts], free_par);  // control is done with tile k - 5
+        PH_MARK(4)
+        float a_reg[kTT / kSWThreads];
+        float2 y_reg[kTT / kSWThreads];
+  #pragma unroll
+        for (int r = 0; r < kTT / kSWThreads; r++) {
+          const int t = wt + r * kSWThreads;
+          a_reg[r] = 0.f;
+          y_reg[r] = make_float2(0.f, 0.f);
+          if (t < nvalid) {
+            const int n = k * kTT + t;
+            float2 y;
+            if (MFQ > 0) {
+              const float2* bp = bhist + t;  // B(n-MFQ+1) .. B(n) are bp[0 .. MFQ-1]
+              y = bp[0];
+  #pragma unroll
+              for (int m = 1; m < MFQ; m++) y = c_add2(y, bp[m]);
+            } else {
+              int m = n - C.mf_q + 1;
+              if (C.mf_rem) {
+                y = phist[(n - C.mf_q) & bmask];
+              } else {
+                y = bhist[m & bmask];
+                m++;
+              }
+              for (; m <= n; m++) y = c_add(y, bhist[m & bmask]);
+            }
+            const float a = cabsf_ref(y.x, y.y);  // gate_impl.cc:130
+            ring_y[ts * kTT + t] = y;
+            ring_a[ts * kTT + t] = a;
+            a_reg[r] = a;
+            y_reg[r] = y;
+          }
+        }
+        PH_MARK(5)
+        split_sync_workers();  // this tile's |y| and y visible to both workers; every block sum has been consumed
+        PH_MARK(6)
+        if (MFQ > 0) {
+          const int t_hi = wt + kSWThreads * (kTT / kSWThreads - 1);  // this thread's last output of the tile
+          if (t_hi >= kTT - (MFQ - 1) && t_hi < nvalid) bhist[t_hi - (kTT - (MFQ - 1))] = b_keep[0];
+        }
+        {
+          // ring differences of this thread's samples, all divisions in flight together (gate_impl.cc:131,141); the
+          // multiply-correct quotients are used when every input of the warp is inside the verified range
+          float xd[kTT / kSWThreads], xr[kTT / kSWThreads], xi[kTT / kSWThreads];
+          bool all_ok = C.win_div_fast && C.dc_div_fast;
+  #pragma unroll
           for (int r = 0; r < kTT / kSWThreads; r++) {
             const int t = wt + r * kSWThreads;
+            xd[r] = xr[r] = xi[r] = 1.0f;
             if (t < nvalid) {
-              ring_d[ts * kTT + t] = f_div_const(xd[r], winlen_f, C.win_recip, C.win_div_fast);
-              etile[(ts * 2 + 0) * kTT + t] = f_div_const(xr[r], dclen_f, C.dc_recip, C.dc_div_fast);
-              etile[(ts * 2 + 1) * kTT + t] = f_div_const(xi[r], dclen_f, C.dc_recip, C.dc_div_fast);
+              int ia = ts * kTT + t - C.win_length;
+              if (ia < 0) ia += kRing;
+              int iy = ts * kTT + t - C.dc_length;
+              if (iy < 0) iy += kRing;
+              const float2 old = ring_y[iy];
+              xd[r] = f_sub(a_reg[r], ring_a[ia]);
+              xr[r] = f_sub(y_reg[r].x, old.x);
+              xi[r] = f_sub(y_reg[r].y, old.y);
+            }
+            all_ok = all_ok && f_div_fast_ok(xd[r]) && f_div_fast_ok(xr[r]) && f_div_fast_ok(xi[r]);
+          }
+          if (__all_sync(0xffffffffu, all_ok)) {
+  #pragma unroll
+            for (int r = 0; r < kTT / kSWThreads; r++) {
+              const int t = wt + r * kSWThreads;
+              if (t < nvalid) {
+                ring_d[ts * kTT + t] = f_div_fast(xd[r], winlen_f, C.win_recip);
+                etile[(ts * 2 + 0) * kTT + t] = f_div_fast(xr[r], dclen_f, C.dc_recip);
+                etile[(ts * 2 + 1) * kTT + t] = f_div_fast(xi[r], dclen_f, C.dc_recip);
+              }
+            }
+          } else {  // an exact zero, a denormal, or an unverified divisor somewhere in the warp: IEEE division
+  #pragma unroll
+            for (int r = 0; r < kTT / kSWThreads; r++) {
+              const int t = wt + r * kSWThreads;
+              if (t < nvalid) {
+                ring_d[ts * kTT + t] = f_div_const(xd[r], winlen_f, C.win_recip, C.win_div_fast);
+                etile[(ts * 2 + 0) * kTT + t] = f_div_const(xr[r], dclen_f, C.dc_recip, C.dc_div_fast);
+                etile[(ts * 2 + 1) * kTT + t] = f_div_const(xi[r], dclen_f, C.dc_recip, C.dc_div_fast);
+              }
             }
           }
         }
