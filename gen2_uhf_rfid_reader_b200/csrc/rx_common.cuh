@@ -73,10 +73,11 @@ __device__ __forceinline__ float f_div_fast(float x, float d, float c)
   const float q = __fmul_rn(x, c);
   return __fmaf_rn(__fmaf_rn(-q, d, x), c, q);
 }
+constexpr float kDivFastMin = 7.9e-31f, kDivFastMax = 1.2e30f;  // verified dividend range of f_div_fast
 __device__ __forceinline__ bool f_div_fast_ok(float x)
 {
   const float ax = fabsf(x);
-  return ax >= 7.9e-31f && ax <= 1.2e30f;
+  return ax >= kDivFastMin && ax <= kDivFastMax;
 }
 
 __device__ __forceinline__ float f_div_const(float x, float d, float c, int fast)

@@ -231,6 +231,24 @@ __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restri
   __syncwarp();
 }
 
+// same, storing |w|^2 (std::norm: re*re + im*im, separately rounded) instead of the sample
+__device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __restrict__ gw, int lo, int count, int n_avail,
+                                                const volatile int* progress = nullptr)
+{
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (progress) {
+    const int need = min(n_avail, lo + count);
+    while (*progress < need) __nanosleep(300);
+    __threadfence_block();
+  }
+  for (int p = lane; p < count; p += 32) {
+    const int g = lo + p;
+    stage_m[p] = (g >= 0 && g < n_avail) ? c_norm(__ldcg(gw + g)) : 0.0f;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
                                                      float2* __restrict__ stage, int stage_cap, WindowDecode& out,
                                                      const volatile int* progress = nullptr)
@@ -319,15 +337,19 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
   const int number_steps = 20;
   const float min_val = c.t_min, max_val = c.t_max;
   const float Tt = f_add(min_val, f_div(f_mul((float)(lane < number_steps ? lane : 0), f_sub(max_val, min_val)), (float)(number_steps - 1)));
+  // Only |w|^2 is needed here (magn_squared_samples, gate_impl.cc:176,186), so the stage holds one float per
+  // sample -- twice the reach of the complex stage: 64 steps per fill.
   float e = 0.0f;
-  for (int i0 = 0; i0 < 256; i0 += 32) {
+  float* stage_m = reinterpret_cast<float*>(stage);
+  const int span = min(2 * stage_cap, (int)(64.0f * max_val + 256.0f * (max_val - min_val)) + 8);
+  for (int i0 = 0; i0 < 256; i0 += 64) {
     const int lo = (int)f_add(f_mul((float)i0, min_val), (float)index);  // smallest index any candidate touches
-    stage_fill(stage, gw, lo, min(stage_cap, (int)(32.0f * max_val + 256.0f * (max_val - min_val)) + 8), n_avail, progress);
+    stage_fill_norm(stage_m, gw, lo, span, n_avail, progress);
     if (lane < number_steps) {
 #pragma unroll 8
-      for (int i = i0; i < i0 + 32; i++) {
+      for (int i = i0; i < i0 + 64; i++) {
         int p = (int)f_add(f_mul((float)i, Tt), (float)index);  // :161
-        e = f_add(e, c_norm(stage[p - lo]));
+        e = f_add(e, stage_m[p - lo]);
       }
     }
   }

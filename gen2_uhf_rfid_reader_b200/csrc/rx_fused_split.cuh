@@ -398,9 +398,14 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
             xi[q] = f_sub(y[q].y, old.y);
           }
         }
-        bool all_ok = C.win_div_fast && C.dc_div_fast;
+        // range test of all twelve dividends at once (3-input min / max)
+        float mx = fabsf(xd[0]), mn = mx;
 #pragma unroll
-        for (int q = 0; q < Q; q++) all_ok = all_ok && f_div_fast_ok(xd[q]) && f_div_fast_ok(xr[q]) && f_div_fast_ok(xi[q]);
+        for (int q = 0; q < Q; q++) {
+          mx = fmaxf(fmaxf(mx, fabsf(xd[q])), fmaxf(fabsf(xr[q]), fabsf(xi[q])));
+          mn = fminf(fminf(mn, fabsf(xd[q])), fminf(fabsf(xr[q]), fabsf(xi[q])));
+        }
+        const bool all_ok = C.win_div_fast && C.dc_div_fast && mn >= kDivFastMin && mx <= kDivFastMax;
         float qd[Q], qr[Q], qi[Q];
         if (__all_sync(0xffffffffu, all_ok)) {
 #pragma unroll
@@ -598,11 +603,19 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const int p = r * 32 + lane;
-          const bool v = p < nv;
-          const float thr = v ? f_mul(davg[p], kThreshFraction) : 0.f;
-          const float a = v ? ta[p] : 0.f;
-          lt[r] = __ballot_sync(0xffffffffu, v && a < thr);
-          gt[r] = __ballot_sync(0xffffffffu, v && a > thr);
+          const float thr = f_mul(davg[p], kThreshFraction);
+          const float a = ta[p];
+          lt[r] = __ballot_sync(0xffffffffu, a < thr);
+          gt[r] = __ballot_sync(0xffffffffu, a > thr);
+        }
+        if (nv < kTT) {  // the segment's last, partial tile: samples past its end compare nothing
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            const int left = nv - r * 32;
+            const unsigned vm = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+            lt[r] &= vm;
+            gt[r] &= vm;
+          }
         }
         if (lane == 0) {
           B.lt_mask[s] = make_uint4(lt[0], lt[1], lt[2], lt[3]);
