@@ -30,16 +30,17 @@ __device__ __forceinline__ void warp_argmax_first(float& v, int& idx)
   }
 }
 
-// CRC-16/CCITT over the first 14 bytes, bitwise like check_crc (tag_decoder_impl.cc:424-440)
+// CRC-16/CCITT (poly 0x1021, init 0xFFFF, final complement) over the first 14 bytes = what check_crc computes bit
+// by bit (tag_decoder_impl.cc:424-440), here a byte per step with the standard shift/xor identity for this polynomial
 __device__ __forceinline__ int crc16_check(const uint32_t bits[4])
 {
   unsigned crc = 0xFFFF;
-#pragma unroll 1
-  for (int i = 0; i < 14; i++) {
-    unsigned byte = (bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
-    crc ^= byte << 8;
 #pragma unroll
-    for (int j = 0; j < 8; j++) crc = (crc & 0x8000u) ? (((crc << 1) ^ 0x1021u) & 0xFFFFu) : ((crc << 1) & 0xFFFFu);
+  for (int i = 0; i < 14; i++) {
+    const unsigned byte = (bits[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
+    unsigned x = ((crc >> 8) ^ byte) & 0xFFu;
+    x ^= x >> 4;
+    crc = ((crc << 8) ^ (x << 12) ^ (x << 5) ^ x) & 0xFFFFu;
   }
   crc = (~crc) & 0xFFFFu;
   unsigned rcvd = bits[3] & 0xFFFFu;  // bytes 14,15

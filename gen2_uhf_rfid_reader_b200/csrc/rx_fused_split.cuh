@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
   float2* dstage = reinterpret_cast<float2*>(smem + A.off_dstage);  // decoder's staging buffer
   float2* const win_base = A.win_scratch + (size_t)seg * A.win_stride;
 
-  for (int i = threadIdx.x; i < A.bhist_size * (C.mf_rem ? 2 : 1); i += kSplitThreads) bhist[i] = make_float2(0.f, 0.f);
+  if (MFQ == 0 || kSWWarps != 1)  // (the consecutive-mapping workers keep their block sums in registers)
+    for (int i = threadIdx.x; i < A.bhist_size * (C.mf_rem ? 2 : 1); i += kSplitThreads) bhist[i] = make_float2(0.f, 0.f);
   for (int i = threadIdx.x; i < kRing; i += kSplitThreads) { ring_y[i] = make_float2(0.f, 0.f); ring_a[i] = 0.f; }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; s++) mbar_init(&B.raw_full[s], 1);
