@@ -595,34 +595,6 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       PH_MARK(2)
       if (lane < 3) chain_inplace(buf, n, acc);
       __syncwarp();
-      if (i < ntiles) {
-        // thresholds of tile i (gate_impl.cc:136,148,154) while the control warp is still busy with tile i-1
-        const int nv = min(kTT, n_out - i * kTT);
-        const float* davg = ring_d + s * kTT;
-        const float* ta = ring_a + s * kTT;
-        unsigned lt[4], gt[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const int p = r * 32 + lane;
-          const float thr = f_mul(davg[p], kThreshFraction);
-          const float a = ta[p];
-          lt[r] = __ballot_sync(0xffffffffu, a < thr);
-          gt[r] = __ballot_sync(0xffffffffu, a > thr);
-        }
-        if (nv < kTT) {  // the segment's last, partial tile: samples past its end compare nothing
-#pragma unroll
-          for (int r = 0; r < 4; r++) {
-            const int left = nv - r * 32;
-            const unsigned vm = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
-            lt[r] &= vm;
-            gt[r] &= vm;
-          }
-        }
-        if (lane == 0) {
-          B.lt_mask[s] = make_uint4(lt[0], lt[1], lt[2], lt[3]);
-          B.gt_mask[s] = make_uint4(gt[0], gt[1], gt[2], gt[3]);
-        }
-      }
       PH_MARK(3)
       // control syncs on chain_done(i) before it publishes elist_ready(i), which this warp needs for
       // iteration i+2: never more than two arrivals outstanding => ids alternate with i
@@ -734,8 +706,28 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
         float* er = etile + (s * 2 + 0) * kTT;
         float* ei = er + kTT;
         if (!terminated) {
-          const uint4 ltv = B.lt_mask[s], gtv = B.gt_mask[s];
-          const unsigned lt[4] = {ltv.x, ltv.y, ltv.z, ltv.w}, gt[4] = {gtv.x, gtv.y, gtv.z, gtv.w};
+          // thresholds of tile i (gate_impl.cc:136,148,154): a < 0.75 avg / a > 0.75 avg per sample, as 128-bit masks.
+          // A tile that lies entirely inside an open window needs none (the gate ignores edges while it is open).
+          unsigned lt[4] = {0u, 0u, 0u, 0u}, gt[4] = {0u, 0u, 0u, 0u};
+          if (!(gate_open && to_ungate - n_samples > nvalid)) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+              const int p = r * 32 + lane;
+              const float thr = f_mul(davg[p], kThreshFraction);
+              const float a = ta[p];
+              lt[r] = __ballot_sync(0xffffffffu, a < thr);
+              gt[r] = __ballot_sync(0xffffffffu, a > thr);
+            }
+            if (nvalid < kTT) {  // the segment's last, partial tile: samples past its end compare nothing
+#pragma unroll
+              for (int r = 0; r < 4; r++) {
+                const int left = nvalid - r * 32;
+                const unsigned vm = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+                lt[r] &= vm;
+                gt[r] &= vm;
+              }
+            }
+          }
           PH_MARK(2)
           int pos = 0;
           while (pos < nvalid) {
