@@ -46,7 +46,6 @@ struct SplitShared {
   int aborted[2];            // the capture ended inside this window: finish the decode, store nothing
   int n_e[kS];               // closed samples in the DC list of each stage
   int n_ev[kS];
-  uint4 lt_mask[kS], gt_mask[kS];  // a < thr / a > thr per sample of the stage (computed by the chain warp)
   TileEvent ev[kS][kMaxTileEvents];
 };
 
