@@ -130,6 +130,32 @@ def _ref_worker(args):
     return t, n
 
 
+def host_cores():
+    """CPUs this process may actually use: affinity mask, capped by the cgroup CPU quota (a container that sees
+    128 logical CPUs but is granted 16 CPUs of time is a 16-core host for this purpose -- more runnable
+    processes than that only get throttled)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = int(q) / int(p)
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except (OSError, ValueError):
+            pass
+    if quota:
+        n = min(n, max(1, int(quota + 0.5)))
+    return max(1, n)
+
+
 def cpu_reference_run(iq_np, segs, steps, warmup, passes_per_step=1):
     """Reference CPU implementation on all host cores: one process per core over disjoint segment ranges
     (the reference keeps its state in a process global, include/rfid/global_vars.h:146).  Timed by wall
@@ -137,7 +163,7 @@ def cpu_reference_run(iq_np, segs, steps, warmup, passes_per_step=1):
     import multiprocessing as mp
     from oracle import refflow
     kind = "reference" if refflow.ref_available(0) else "port"
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     nseg = segs.size
     _G["iq"] = np.ascontiguousarray(iq_np)
     jobs = []
@@ -159,8 +185,9 @@ def cpu_reference_run(iq_np, segs, steps, warmup, passes_per_step=1):
     total = sum(times)
     return {"kind": kind, "cores": cores, "ms_per_step": 1e3 * total / max(1, len(times)),
             "value": n_samples * len(times) / total / 1e6, "windows_last_step": windows,
-            "sample": "cfg2 capture: %d segments (%.1f M samples) split over %d processes, %d pass(es) per step, %d steps"
-                      % (nseg, n_samples / passes_per_step / 1e6, cores, passes_per_step, len(times))}
+            "sample": "cfg2 capture: %d segments (%.1f M samples) split over %d processes (= usable CPUs: affinity and "
+                      "cgroup quota; os.cpu_count() = %d), %d pass(es) per step, %d steps"
+                      % (nseg, n_samples / passes_per_step / 1e6, cores, os.cpu_count() or 1, passes_per_step, len(times))}
 
 
 def main():
@@ -191,7 +218,8 @@ def main():
         if rank != 0:
             return 0
         cap = synth.make_capture(args.rounds, seed=1234, device="cpu")
-        r = cpu_reference_run(cap["iq"].numpy(), cap["segments"], args.steps, args.warmup)
+        # each step = 8 passes over the 1000-round capture (bounded sample: ~0.05-0.1 s per step on a 16-CPU host)
+        r = cpu_reference_run(cap["iq"].numpy(), cap["segments"], args.steps, args.warmup, passes_per_step=8)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MSamples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -336,7 +364,7 @@ def main():
         cpu_b = None
         if not args.no_cpu_baseline:
             cap_cpu = synth.make_capture(args.rounds, seed=1234, device="cpu")
-            # bounded sample: ~20-30 s of CPU work = 6 x 40 passes over the 1000-round capture, all cores
+            # bounded sample: ~20-30 s of CPU work = 6 x 40 passes over the 1000-round capture, all usable CPUs
             r = cpu_reference_run(cap_cpu["iq"].numpy(), cap_cpu["segments"], steps=5, warmup=1, passes_per_step=40)
             cpu_b = {"value": r["value"], "unit": "MSamples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         line = {"metric": METRIC, "value": value, "unit": "MSamples/s", "n_gpus": world, "steps": args.steps,
