@@ -25,11 +25,15 @@ def load_library():
     if _lib is not None:
         return _lib
     path = LIB
-    try:
-        path = build_library()
-    except Exception:
-        if not os.path.exists(LIB):
-            raise
+    override = os.environ.get("RFID_B200_LIB")   # developer aid: a library built with other flags (tools/variants.sh)
+    if override:
+        path = override
+    else:
+        try:
+            path = build_library()
+        except Exception:
+            if not os.path.exists(LIB):
+                raise
     if not os.path.exists(path):
         raise RfidB200Error("librfid_b200.so is missing: run `python -m gen2_uhf_rfid_reader_b200.build` "
                             "(there is no CPU fallback)")

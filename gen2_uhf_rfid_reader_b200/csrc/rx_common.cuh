@@ -152,11 +152,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 }
 // spin a few times (the phase is usually complete or about to be), then back off so that a waiting warp
 // does not take issue slots away from the latency-critical warps of the co-resident CTAs
+#ifndef RFID_B200_MBAR_BACKOFF_NS
+#define RFID_B200_MBAR_BACKOFF_NS 200
+#endif
+#ifndef RFID_B200_MBAR_SPINS
+#define RFID_B200_MBAR_SPINS 4
+#endif
+constexpr unsigned kMbarBackoffNs = RFID_B200_MBAR_BACKOFF_NS;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < RFID_B200_MBAR_SPINS; i++)
     if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+  while (!mbar_try_wait(bar, parity)) __nanosleep(kMbarBackoffNs);
 }
 // wait for a phase that is not on this warp's critical path: let the hardware park the warp
 // (suspend-time hint, ns) instead of burning issue slots that the sequencer warps need

@@ -215,6 +215,9 @@ __host__ __device__ inline int decode_stage_samples(float n_tag_bit)
 // `progress` (may be null): number of window samples the producer has published so far; the fill waits until
 // the range it is about to read exists.  This is what lets the decoder work on a window WHILE it is still being
 // gated (streaming decode), instead of starting when the window closes.
+#ifndef RFID_B200_PROGRESS_NS
+#define RFID_B200_PROGRESS_NS 300
+#endif
 __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail,
                                            const volatile int* progress = nullptr)
 {
@@ -222,7 +225,7 @@ __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restri
   __syncwarp();
   if (progress) {
     const int need = min(n_avail, lo + count);
-    while (*progress < need) __nanosleep(300);
+    while (*progress < need) __nanosleep(RFID_B200_PROGRESS_NS);
     __threadfence_block();  // the samples were written (and fenced, CTA scope) before the counter moved
   }
   for (int p = lane; p < count; p += 32) {
@@ -240,7 +243,7 @@ __device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __
   __syncwarp();
   if (progress) {
     const int need = min(n_avail, lo + count);
-    while (*progress < need) __nanosleep(300);
+    while (*progress < need) __nanosleep(RFID_B200_PROGRESS_NS);
     __threadfence_block();
   }
   for (int p = lane; p < count; p += 32) {

@@ -69,10 +69,13 @@ __device__ __forceinline__ void bar2_arrive(int parity)
 }
 
 // a wait that is off the critical path: poll rarely
+#ifndef RFID_B200_LAZY_NS
+#define RFID_B200_LAZY_NS 2000
+#endif
 __device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity)
 {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(2000);
+  while (!mbar_try_wait(bar, parity)) __nanosleep(RFID_B200_LAZY_NS);
 }
 // a wait on the critical path: poll back to back
 __device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity)
