@@ -88,3 +88,35 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("does not touch oracle/", "").lower(), os.path.join(dirpath, f)
+
+
+def test_new_entry_points_reject_null_context_and_have_sane_defaults():
+    """ingest / TX synthesiser / simulator entry points: argument checks come before any CUDA call"""
+    lib = capi.load_library()
+    n, ns = C.c_int(0), C.c_size_t(0)
+    segs = np.zeros(4, dtype=abi.SEGMENT_DTYPE)
+    x = np.zeros(8, dtype=np.float32)
+    assert lib.rfid_b200_segment_capture(None, x.ctypes.data, 4, None, segs.ctypes.data, 4, C.byref(n), None) == abi.EINVAL
+    assert lib.rfid_b200_ingest_capture_host(None, x.ctypes.data, 4, None, 2, segs.ctypes.data, 4, C.byref(n), None, None) == abi.EINVAL
+    scr = np.zeros(1, dtype=abi.TX_COMMAND_DTYPE)
+    assert lib.rfid_b200_tx_synth(None, scr.ctypes.data, 1, 1000000, None, 0, C.byref(ns), None) == abi.EINVAL
+    sim = capi.default_sim()
+    assert lib.rfid_b200_sim_segment_length(None, C.byref(sim)) == abi.EINVAL
+    assert lib.rfid_b200_sim_capture(None, C.byref(sim), 0, 1, None, None, None, None) == abi.EINVAL
+    # defaults: SURVEY 8d signal model, gate_impl.cc:164 pulse rule
+    assert (sim.n_tags, sim.closed_loop, sim.dac_rate) == (1, 1, 1000000)
+    assert abs(sim.segment_us - 8480.0) < 1e-3 and abs(sim.leak_re - 0.2846) < 1e-6 and abs(sim.noise_sigma - 0.003) < 1e-7
+    sp = capi.default_segmenter()
+    assert (sp.min_pulses, sp.commands_per_segment) == (6, 2) and sp.lead_us < sp.gap_us
+    assert C.sizeof(abi.SimParams) == 64 and C.sizeof(abi.Segmenter) == 32 and abi.SIM_TRUTH_DTYPE.itemsize == 48
+
+
+def test_sass_of_the_new_kernels_is_present():
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.check_output(["cuobjdump", "-sass", capi.LIB], text=True)
+    for k in ("ingest_mask", "ingest_scan", "ingest_bursts", "tx_synth_kernel", "sim_slot_kernel", "rx_fused_split_kernel"):
+        assert k in out, k
+    assert "FMNMX3" in out and "FADD2" in out      # 3-input min/max range test, packed f32x2 adds of the worker
