@@ -218,9 +218,17 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
 #else
 #define PH_END(slot)
 #endif
-  // roles rotate over the hardware warps so that the chain warps of co-resident CTAs spread over the SM
-  // sub-partitions: 0 chain, 1 control, 2..3 workers, 4 decoder
-  const int role = ((threadIdx.x >> 5) + blockIdx.x) % kSplitWarps;
+  // roles: 0 chain, 1 control, 2.. workers, last decoder
+  // Fixed role per warp slot (nibble w of kRolePerm = role of warp w): every CTA puts the same role on the same SM
+  // sub-partition, so each sub-partition's instruction cache holds one role's code.  Measured on the 1000-segment
+  // benchmark (tools/variants.sh): rotating the roles by the CTA's ordinal on its SM 81.5 us, rotating by blockIdx
+  // 70.3 us, fixed slots 66-71 us depending on the order, worker / chain / control / decoder 66.1 us.
+#ifndef RFID_B200_ROLE_PERM
+#define RFID_B200_ROLE_PERM 0x2013
+#endif
+  static_assert(kSplitWarps == 4 || kSplitWarps == 5, "role table");
+  const int role = kSplitWarps == 4 ? (RFID_B200_ROLE_PERM >> (4 * (3 - (threadIdx.x >> 5)))) & 0xF
+                                    : ((threadIdx.x >> 5) + blockIdx.x) % kSplitWarps;
   const RxConfig& C = A.cfg;
   const rfid_b200_segment sg = A.segs[seg];
   const int n_out = (int)(sg.length / DECIM);

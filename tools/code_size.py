@@ -4,7 +4,7 @@ import os, re, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "gen2_uhf_rfid_reader_b200", "csrc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-cubin"]
-variants = {"full": None, "no workers": "if (role == 2 || role == 3) {", "no chain": "} else if (role == 0) {",
+variants = {"full": None, "no workers": "if (role >= 2 && role < 2 + kSWWarps) {", "no chain": "} else if (role == 0) {",
             "no control": "} else if (role == 1) {", "no decoder": "DECODER"}
 for name, pat in variants.items():
     d = "/tmp/sz_%d" % os.getpid()
@@ -20,7 +20,7 @@ for name, pat in variants.items():
         s = s[:i] + s[j:]
     elif pat:
         assert pat in s
-        s = s.replace(pat, pat.replace("role == 2 || role == 3", "false").replace("role == 0", "false").replace("role == 1", "false"))
+        s = s.replace(pat, pat.replace("role >= 2 && role < 2 + kSWWarps", "false").replace("role == 0", "false").replace("role == 1", "false"))
     open(f, "w").write(s)
     out = os.path.join(d, "k.cubin")
     subprocess.check_call(["nvcc"] + FLAGS + ["-o", out, os.path.join(d, "gen2_uhf_rfid_reader_b200", "csrc", "rfid_b200.cu")],
