@@ -219,16 +219,27 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
 #define PH_END(slot)
 #endif
   // roles: 0 chain, 1 control, 2.. workers, last decoder
-  // Fixed role per warp slot (nibble w of kRolePerm = role of warp w): every CTA puts the same role on the same SM
-  // sub-partition, so each sub-partition's instruction cache holds one role's code.  Measured on the 1000-segment
-  // benchmark (tools/variants.sh): rotating the roles by the CTA's ordinal on its SM 81.5 us, rotating by blockIdx
-  // 70.3 us, fixed slots 66-71 us depending on the order, worker / chain / control / decoder 66.1 us.
+  // Fixed role per warp of the CTA (nibble w of the table = role of warp w).  The hardware already places the four
+  // warps of successive CTAs on the SM's warp slots with a rotating offset (tools/warpmap.py: CTA k's warp w gets slot
+  // 4k + (w + c_k) % 4), so with a fixed table every sub-partition ends up with one or two warps of each role.  Rotating
+  // the roles in software on top of that can cancel the hardware's rotation and stack all running-sum warps of an SM on
+  // one sub-partition.  Measured on the 1000-segment benchmark (tools/variants.sh): rotating by the CTA's ordinal on
+  // its SM 81.5 us, rotating by blockIdx 70.3 us, fixed tables 66-71 us depending on the order, worker / chain /
+  // control / decoder 66.1 us.
 #ifndef RFID_B200_ROLE_PERM
 #define RFID_B200_ROLE_PERM 0x2013
 #endif
   static_assert(kSplitWarps == 4 || kSplitWarps == 5, "role table");
   const int role = kSplitWarps == 4 ? (RFID_B200_ROLE_PERM >> (4 * (3 - (threadIdx.x >> 5)))) & 0xF
                                     : ((threadIdx.x >> 5) + blockIdx.x) % kSplitWarps;
+#ifdef RFID_B200_PHASE_PROFILE
+  if (lane == 0 && A.window_tap) {  // where did the hardware put this warp?  (slot 24*nseg + 4*cta + role) = smid << 16 | warpid
+    unsigned smid, wid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    reinterpret_cast<long long*>(A.window_tap)[(size_t)gridDim.x * 24 + (size_t)blockIdx.x * 4 + role] = (long long)((smid << 16) | wid);
+  }
+#endif
   const RxConfig& C = A.cfg;
   const rfid_b200_segment sg = A.segs[seg];
   const int n_out = (int)(sg.length / DECIM);
