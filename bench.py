@@ -198,6 +198,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rounds", type=int, default=N_ROUNDS, help="inventory rounds (segments) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generator", default="torch", choices=["torch", "native"],
+                    help="workload generator of our arm: the torch model (same samples as the CPU reference arm) or the "
+                         "library's CUDA closed-loop slot simulator (rfid_b200_sim_capture)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -211,7 +214,8 @@ def main():
                           % (args.rounds, seg_len),
               "rounds_per_gpu": args.rounds, "segment_samples": seg_len, "fixed_q": 0,
               "l2": "inputs larger than L2: %d distinct captures of %.0f MB cycled" % (NBUF, args.rounds * seg_len * 8 / 1e6),
-              "parallelism": "segments sharded over %d GPU(s), one all-gather of all decoded records at the end of the timed region" % world}
+              "parallelism": "segments sharded over %d GPU(s), one all-gather of all decoded records at the end of the timed region" % world,
+              "generator": args.generator}
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
@@ -245,12 +249,22 @@ def main():
     rx = capi.Gen2Rx(device=local_rank)
     caps, truths, seg_dev = [], [], None
     for b in range(NBUF):
-        cap = synth.make_capture(args.rounds, seed=1234 + 17 * b, first_segment=first, device=dev)
-        caps.append(cap["iq"])
-        truths.append(cap["truth"])
-        if seg_dev is None:
-            segs_np = cap["segments"]
-            seg_dev = capi.segments_to_device(segs_np, dev)
+        if args.generator == "native":
+            sim = capi.default_sim(seed=1234 + 17 * b, segment_us=SEG_US)
+            cap = rx.sim_capture(sim, args.rounds, first_segment=first, device=dev)
+            tr = cap["truth"].cpu().numpy().view(abi.SIM_TRUTH_DTYPE).reshape(-1)
+            caps.append(cap["iq"])
+            truths.append({"rn16": tr["acked_rn16"].astype(np.int64), "epc": tr["epc"]})
+            if seg_dev is None:
+                seg_dev = cap["segs"]
+                segs_np = cap["segs"].cpu().numpy().view(abi.SEGMENT_DTYPE).reshape(-1)
+        else:
+            cap = synth.make_capture(args.rounds, seed=1234 + 17 * b, first_segment=first, device=dev)
+            caps.append(cap["iq"])
+            truths.append(cap["truth"])
+            if seg_dev is None:
+                segs_np = cap["segments"]
+                seg_dev = capi.segments_to_device(segs_np, dev)
     n_raw = caps[0].numel()
     # every step keeps its records on the device; ONE all-gather of all of them closes the timed region
     # (north star: "a single NCCL gather of decoded EPCs at the end")
