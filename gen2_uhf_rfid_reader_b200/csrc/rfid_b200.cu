@@ -192,7 +192,7 @@ fused_fn pick_kernel(const RxConfig& c)
     if (c.mf_rem == 0 && c.mf_q == 5) return rx_fused_split_kernel<5, 5>;  // the reference configuration: 25 taps
     return rx_fused_split_kernel<5, 0>;
   }
-  return rx_fused_kernel<5, 0, false>;  // long rings (raw rates above 5 MS/s) and any tap count
+  return rx_fused_kernel<5, 0>;  // long rings (raw rates above 5 MS/s) and any tap count
 }
 
 int grow(rfid_b200_ctx* ctx, void** p, size_t* have, size_t need)

@@ -203,10 +203,9 @@ __device__ __forceinline__ void issue_tile_load(const FusedArgs& A, const rfid_b
 }
 
 // MFQ > 0: ntaps == MFQ * DECIM (compile-time unrolled block sums); MFQ == 0: generic ntaps.
-// SPEC: win_length <= kTT and dc_length <= kTT (true up to 5 MS/s raw): the amplitude / DC ring lookbacks
-// come straight from the time-indexed tile stages and the workers pre-compute the DC-ring differences, so
-// on a tile without gate activity the sequencer only runs its running sums.
-template <int DECIM, int MFQ, bool SPEC>
+// This kernel keeps explicit amplitude / closed-sample rings of any length (raw rates above 5 MS/s, where the
+// reference's 250 us / 120 us windows are longer than a tile); rx_fused_split_kernel is the fast path below that.
+template <int DECIM, int MFQ>
 __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedArgs A)
 {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -230,8 +229,6 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
   float2* ycl = reinterpret_cast<float2*>(smem + A.off_ycl);
   float* e_re = reinterpret_cast<float*>(smem + A.off_e);
   float* e_im = e_re + kTT + 16;
-  float* etile = reinterpret_cast<float*>(smem + A.off_etile);  // [stage][re|im][kTT]
-  float2* snap = reinterpret_cast<float2*>(smem + A.off_snap);
   // ungated window samples go to a per-segment global scratch (written once, read once by the decoder warp
   // of the same CTA a few microseconds later: L2 traffic, not shared memory -- that is what lets 8 CTAs fit an SM)
   float2* const win_base = A.win_scratch + (size_t)seg * A.win_stride;
@@ -239,12 +236,8 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
   // ---- init: zero the history rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56;
   //      x[<0] = +0 for the matched filter), set up the TMA barriers
   for (int i = threadIdx.x; i < A.bhist_size * (C.mf_rem ? 2 : 1); i += kFusedThreads) bhist[i] = make_float2(0.f, 0.f);
-  if (SPEC) {
-    for (int i = threadIdx.x; i < kTileStages * kTT; i += kFusedThreads) { tile_y[i] = make_float2(0.f, 0.f); tile_a[i] = 0.f; }
-  } else {
-    for (int i = threadIdx.x; i < A.ahist_size; i += kFusedThreads) ahist[i] = 0.f;
-    for (int i = threadIdx.x; i < A.ycl_size; i += kFusedThreads) ycl[i] = make_float2(0.f, 0.f);
-  }
+  for (int i = threadIdx.x; i < A.ahist_size; i += kFusedThreads) ahist[i] = 0.f;
+  for (int i = threadIdx.x; i < A.ycl_size; i += kFusedThreads) ycl[i] = make_float2(0.f, 0.f);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; s++) mbar_init(&B.raw_full[s], 1);
     for (int s = 0; s < 2; s++) { mbar_init(&B.win_ready[s], 1); mbar_init(&B.win_free[s], 1); }
@@ -261,7 +254,7 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
         issue_tile_load<DECIM>(A, sg, k, raw + (size_t)k * A.raw_stage_samples, &B.raw_full[k]);
     }
     const int bmask = A.bhist_size - 1, amask = A.ahist_size - 1;
-    const float winlen_f = (float)C.win_length, dclen_w = (float)C.dc_length;
+    const float winlen_f = (float)C.win_length;
     PH_DECL
     for (int k = 0; k < ntiles; k++) {
       const int rs = k % kRawStages, ts = k % kTileStages;
@@ -339,7 +332,7 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
           const float a = cabsf_ref(y.x, y.y);  // gate_impl.cc:130
           tile_y[ts * kTT + t] = y;
           tile_a[ts * kTT + t] = a;
-          if (!SPEC) ahist[n & amask] = a;
+          ahist[n & amask] = a;
           a_reg[r] = a;
           y_reg[r] = y;
         }
@@ -353,21 +346,7 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
         const int t = wt + r * kWorkerThreads;
         if (t < nvalid) {
           const int n = k * kTT + t;
-          if (SPEC) {
-            // the tile stages are one time-indexed ring of kTileStages*kTT samples (tile k-1 is still resident)
-            int ia = ts * kTT + t - C.win_length;
-            if (ia < 0) ia += kTileStages * kTT;
-            tile_d[ts * kTT + t] = f_div(f_sub(a_reg[r], tile_a[ia]), winlen_f);
-            // (in - dc_samples[dc_index]) / dc_length assuming the previous dc_length samples were all closed
-            // (gate_impl.cc:141); the sequencer redoes the few samples for which that is not true
-            int iy = ts * kTT + t - C.dc_length;
-            if (iy < 0) iy += kTileStages * kTT;
-            const float2 old = tile_y[iy];
-            etile[(ts * 2 + 0) * kTT + t] = f_div(f_sub(y_reg[r].x, old.x), dclen_w);
-            etile[(ts * 2 + 1) * kTT + t] = f_div(f_sub(y_reg[r].y, old.y), dclen_w);
-          } else {
-            tile_d[ts * kTT + t] = f_div(f_sub(a_reg[r], ahist[(n - C.win_length) & amask]), winlen_f);
-          }
+          tile_d[ts * kTT + t] = f_div(f_sub(a_reg[r], ahist[(n - C.win_length) & amask]), winlen_f);
         }
       }
       __threadfence_block();
@@ -409,8 +388,8 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
       if (k < ntiles) bar_sync_stage<BAR_TILE_FULL>(ts, 96);
       PH_MARK(1)
       // ---- 1. the three recurrences, one pass: avg_ampl over tile k, dc_est over tile k-1's closed samples
-      float* pe_re = SPEC ? etile + (((k + kTileStages - 1) % kTileStages) * 2 + 0) * kTT : e_re;  // tile k-1's list
-      float* pe_im = SPEC ? pe_re + kTT : e_im;
+      float* pe_re = e_re;  // tile k-1's list
+      float* pe_im = e_im;
       if (lane < 3) chain_inplace(lane == 0 ? davg : (lane == 1 ? pe_re : pe_im), lane == 0 ? nvalid : n_e, acc);
       __syncwarp();
       PH_MARK(2)
@@ -511,47 +490,13 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
             // ---- DC tracker inputs for the closed run [run_start, pos) (gate_impl.cc:141-143); the run
             //      includes the trigger sample, as in the reference (the update precedes the open test)
             const int len = pos - run_start;
-            if (SPEC) {
-              float* er = etile + (ts * 2 + 0) * kTT;
-              float* ei = er + kTT;
-              if (run_start == 0 && pos == nvalid && !opened && closed_since >= C.dc_length) {
-                // quiet tile: the workers' differences are exact, nothing to do
-              } else {
-                // rebuild the list for this run: ring lookback = snapshot taken at the last gate opening for
-                // the first dc_length closed samples after a window, else the sample dc_length earlier
-                for (int j = lane; j < len; j += 32) {
-                  const int i = run_start + j, m = closed_since + j;
-                  const float2 yv = ty[i];
-                  float2 old;
-                  if (m < C.dc_length) {
-                    old = snap[m];
-                  } else {
-                    int iy = ts * kTT + i - C.dc_length;
-                    if (iy < 0) iy += kTileStages * kTT;
-                    old = tile_y[iy];
-                  }
-                  er[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
-                  ei[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
-                }
-              }
-              closed_since = min(closed_since + len, 1 << 24);
-              if (opened) {
-                // the dc ring as it stands when the gate opens: the last dc_length closed samples
-                for (int j = lane; j < C.dc_length; j += 32) {
-                  int iy = ts * kTT + (pos - 1) - C.dc_length + 1 + j;
-                  if (iy < 0) iy += kTileStages * kTT;
-                  snap[j] = tile_y[iy];
-                }
-              }
-            } else {
-              for (int j = lane; j < len; j += 32) ycl[(n_closed + j) & ymask] = ty[run_start + j];
-              __syncwarp();
-              for (int j = lane; j < len; j += 32) {
-                const float2 yv = ty[run_start + j];
-                const float2 old = ycl[(n_closed + j - C.dc_length) & ymask];
-                e_re[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
-                e_im[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
-              }
+            for (int j = lane; j < len; j += 32) ycl[(n_closed + j) & ymask] = ty[run_start + j];
+            __syncwarp();
+            for (int j = lane; j < len; j += 32) {
+              const float2 yv = ty[run_start + j];
+              const float2 old = ycl[(n_closed + j - C.dc_length) & ymask];
+              e_re[n_e + j] = f_div(f_sub(yv.x, old.x), dclen_f);
+              e_im[n_e + j] = f_div(f_sub(yv.y, old.y), dclen_f);
             }
             n_closed += len;
             n_e += len;
