@@ -7,7 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librfid_b200.so")
 SOURCES = ["rfid_b200.cu"]
-HEADERS = ["rx_common.cuh", "rx_decode.cuh", "rx_fused.cuh", "rx_fused_split.cuh", "rx_block.cuh", "../../include/rfid_b200.h"]
+import glob
+HEADERS = sorted(os.path.basename(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))) + ["../../include/rfid_b200.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               # no FMA contraction: the reference's x86-64 objects contain none

@@ -17,6 +17,7 @@
 #include "rx_fused.cuh"
 #include "rx_fused_split.cuh"
 #include "rx_ingest.cuh"
+#include "rx_pack.cuh"
 #include "tx_synth.cuh"
 
 using namespace rfid_b200;
@@ -36,6 +37,9 @@ struct rfid_b200_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   float kernel_ms;
   int kernel_launches;
+  int sm_count;
+  int pack_g_override;  // RFID_B200_PACK_G (developer aid): segments per CTA of the pack kernel, 0 = automatic
+  bool pack_disabled;   // RFID_B200_KERNEL=split: keep the one-CTA-per-segment kernels for every configuration
   // host-mode staging buffers
   void* d_iq; size_t d_iq_bytes;
   void* d_segs; size_t d_segs_bytes;
@@ -184,6 +188,34 @@ void make_layout(const RxConfig& c, FusedArgs& L)
   L.smem_bytes = off;
 }
 
+// rx_pack_kernel serves the reference configuration (block-sum matched filter with 5 blocks of 5, rings inside a tile)
+bool pack_ok(const RxConfig& c) { return c.decim == 5 && c.mf_rem == 0 && c.mf_q == 5 && fast_path_ok(c); }
+
+// shared-memory carve-up of rx_pack_kernel for G segments per CTA
+void make_layout_pack(const RxConfig& c, int G, PackArgs& L)
+{
+  L.G = G;
+  L.raw_stage_samples = c.decim * kTT + 2;
+  int o = 0;
+  L.o_raw = o; o = align_up(o + kPRawStages * L.raw_stage_samples * 8, 16);
+  L.o_ring_y = o; o += kPRing * 8;
+  L.o_ring_a = o; o += kPRing * 4;
+  L.o_snap = o; o = align_up(o + c.dc_length * 8, 16);
+  L.dstage_samples = decode_stage_samples(c.n_tag_bit_f);
+  if (L.dstage_samples < c.len_rn16) L.dstage_samples = align_up(c.len_rn16, 8);  // an RN16 window is staged whole
+  L.o_dstage = o; o = align_up(o + L.dstage_samples * 8, 128);
+  L.seg_bytes = o;
+  int off = 0;
+  L.off_dA = off; off += 2 * G * kPChainBuf * 4;
+  L.off_dD = off; off += kPS * 2 * G * kPChainBuf * 4;
+  L.off_seg = align_up(off, 128);
+  L.smem_bytes = L.off_seg + G * L.seg_bytes;
+  L.rn16_pad = align_up(c.len_rn16, 16);
+  L.win_stride = L.rn16_pad + align_up(c.len_epc, 16);
+}
+
+int pack_segments_per_cta(const rfid_b200_ctx* ctx, int nseg);
+
 typedef void (*fused_fn)(const FusedArgs);
 fused_fn pick_kernel(const RxConfig& c)
 {
@@ -205,6 +237,18 @@ int grow(rfid_b200_ctx* ctx, void** p, size_t* have, size_t need)
   if (e != cudaSuccess) { ctx->last_error = "cudaMalloc failed"; cudaGetLastError(); return RFID_B200_ENOMEM; }
   *have = want;
   return RFID_B200_OK;
+}
+
+// Segments per CTA of rx_pack_kernel: as few CTAs as fill the device once (one CTA per SM, every SM busy for the
+// whole launch); larger batches run kPMaxSeg per CTA in several waves.
+int pack_segments_per_cta(const rfid_b200_ctx* ctx, int nseg)
+{
+  if (ctx->pack_g_override > 0) return ctx->pack_g_override;
+  const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+  int g = (nseg + sms - 1) / sms;
+  if (g < 1) g = 1;
+  if (g > kPMaxSeg) g = kPMaxSeg;
+  return g;
 }
 
 void drain_timing(rfid_b200_ctx* ctx)
@@ -290,6 +334,22 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
     e = cudaMemcpyAsync(ctx->d_gate, &init, offsetof(GateState, win_samples), cudaMemcpyHostToDevice, ctx->stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  ctx->sm_count = prop.multiProcessorCount;
+  {
+    const char* ev = getenv("RFID_B200_PACK_G");
+    ctx->pack_g_override = ev ? atoi(ev) : 0;
+    if (ctx->pack_g_override < 0 || ctx->pack_g_override > kPMaxSeg) ctx->pack_g_override = 0;
+    const char* kv = getenv("RFID_B200_KERNEL");
+    ctx->pack_disabled = kv && strcmp(kv, "split") == 0;
+  }
+  if (e == cudaSuccess && pack_ok(cfg)) {
+    PackArgs pl;
+    make_layout_pack(cfg, kPMaxSeg, pl);
+    e = cudaFuncSetAttribute((const void*)rx_pack_kernel<5, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)rx_pack_kernel<5, 5>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
+  }
   fused_fn fn = pick_kernel(cfg);
   if (e == cudaSuccess && fn)
     e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->layout.smem_bytes);
@@ -395,7 +455,17 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, s));
   }
-  fn<<<nseg, fast_path_ok(ctx->cfg) ? kSplitThreads : kFusedThreads, A.smem_bytes, s>>>(A);
+  if (pack_ok(ctx->cfg) && !ctx->pack_disabled) {
+    PackArgs P;
+    memset(&P, 0, sizeof(P));
+    make_layout_pack(ctx->cfg, pack_segments_per_cta(ctx, nseg), P);
+    P.iq = A.iq; P.n_raw = A.n_raw; P.segs = A.segs; P.nseg = nseg; P.max_windows = A.max_windows;
+    P.results = A.results; P.counts = A.counts; P.window_tap = A.window_tap; P.win_scratch = A.win_scratch;
+    P.cfg = ctx->cfg;
+    rx_pack_kernel<5, 5><<<(nseg + P.G - 1) / P.G, 32 * (2 * P.G + 1), P.smem_bytes, s>>>(P);
+  } else {
+    fn<<<nseg, fast_path_ok(ctx->cfg) ? kSplitThreads : kFusedThreads, A.smem_bytes, s>>>(A);
+  }
   CK(cudaGetLastError());
   if (ctx->timing) {
     CK(cudaEventRecord(e1, s));
