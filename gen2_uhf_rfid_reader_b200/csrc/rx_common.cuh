@@ -100,6 +100,31 @@ __device__ __forceinline__ float cabsf_ref(float re, float im)
   return __double2float_rn(__dsqrt_rn(s));
 }
 
+// The same value without the branches of __dsqrt_rn, so that several evaluations interleave: s as above, one Newton step
+// on rsqrt.approx.f64 (relative error after the step < 2^-40), rounded to float.  That equals
+// (float)sqrt_rn(s) whenever the approximation is farther than its own error bound from every float rounding boundary
+// (the mid-points between adjacent floats, 29 bits below the double's leading bit); `risky` reports the rest -- values
+// within 2^-38 of a boundary (one sample in 2^13), zero, and magnitudes where the float result would be subnormal or
+// infinite -- for which the caller evaluates cabsf_ref.  tools/micro/cabs_check.cu compares the pair against cabsf_ref.
+__device__ __forceinline__ float cabsf_quick(float re, float im, bool& risky)
+{
+  const double dr = (double)re, di = (double)im;
+  const double s = __fma_rn(di, di, __dmul_rn(dr, dr));
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  double g = __dmul_rn(s, y);
+  const double h = __dmul_rn(0.5, y);
+  const double r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g);
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(g);
+  const unsigned low = (unsigned)bits & 0x1FFFFFFFu;                 // the 29 bits a float does not keep
+  const unsigned hi = (unsigned)(bits >> 32);
+  const bool near_mid = (unsigned)(low - 0x10000000u + 0x8000u) < 0x10000u;   // |low - mid| < 2^15  (2^-38 relative)
+  const bool range_ok = hi > 0x38200000u && hi < 0x47E00000u;       // 2^-125 < g < 2^127: normal float, finite, not NaN
+  risky = near_mid || !range_ok;
+  return __double2float_rn(g);
+}
+
 __device__ __forceinline__ float2 c_add(float2 a, float2 b) { return make_float2(f_add(a.x, b.x), f_add(a.y, b.y)); }
 // complex add as ONE packed instruction (sm_100 add.rn.f32x2: two independent IEEE round-to-nearest adds)
 __device__ __forceinline__ float2 c_add2(float2 a, float2 b)
@@ -177,6 +202,17 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
         : "memory");
   } while (!ok);
+}
+// one try_wait with a suspend-time hint: true when the phase of parity `parity` has completed; false after (about) hint_ns
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
 }
 // 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar`
 // (SASS: UBLKCP).  dst/src 16-byte aligned, bytes a multiple of 16.

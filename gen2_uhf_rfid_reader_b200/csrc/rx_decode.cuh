@@ -218,16 +218,31 @@ __host__ __device__ inline int decode_stage_samples(float n_tag_bit)
 #ifndef RFID_B200_PROGRESS_NS
 #define RFID_B200_PROGRESS_NS 300
 #endif
+// How the decoder waits for window samples that are still being gated: `counter` = samples published so far.  With a
+// doorbell (an mbarrier the producer arrives on after every publication) the waiting warp is parked by the hardware;
+// without one it polls the counter with a sleep in between.  The counter, not the doorbell's phase, decides: every wait
+// is bounded (suspend hint), so a phase that was rung before the warp looked only costs one time-out.
+struct ProgressWait {
+  const volatile int* counter;
+  uint64_t* bell;
+  uint32_t seen;
+};
+__device__ __forceinline__ void progress_wait(ProgressWait* pw, int need)
+{
+  if (!pw || !pw->counter) return;
+  while (*pw->counter < need) {
+    if (pw->bell) { if (mbar_try_wait_hint(pw->bell, pw->seen & 1u, 2000)) pw->seen++; }
+    else __nanosleep(RFID_B200_PROGRESS_NS);
+  }
+  __threadfence_block();  // the samples were written (and fenced, CTA scope) before the counter moved
+}
+
 __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail,
-                                           const volatile int* progress = nullptr)
+                                           ProgressWait* progress = nullptr)
 {
   const int lane = threadIdx.x & 31;
   __syncwarp();
-  if (progress) {
-    const int need = min(n_avail, lo + count);
-    while (*progress < need) __nanosleep(RFID_B200_PROGRESS_NS);
-    __threadfence_block();  // the samples were written (and fenced, CTA scope) before the counter moved
-  }
+  progress_wait(progress, min(n_avail, lo + count));
   for (int p = lane; p < count; p += 32) {
     const int g = lo + p;
     stage[p] = (g >= 0 && g < n_avail) ? __ldcg(gw + g) : make_float2(0.f, 0.f);
@@ -237,15 +252,11 @@ __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restri
 
 // same, storing |w|^2 (std::norm: re*re + im*im, separately rounded) instead of the sample
 __device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __restrict__ gw, int lo, int count, int n_avail,
-                                                const volatile int* progress = nullptr)
+                                                ProgressWait* progress = nullptr)
 {
   const int lane = threadIdx.x & 31;
   __syncwarp();
-  if (progress) {
-    const int need = min(n_avail, lo + count);
-    while (*progress < need) __nanosleep(RFID_B200_PROGRESS_NS);
-    __threadfence_block();
-  }
+  progress_wait(progress, min(n_avail, lo + count));
   for (int p = lane; p < count; p += 32) {
     const int g = lo + p;
     stage_m[p] = (g >= 0 && g < n_avail) ? c_norm(__ldcg(gw + g)) : 0.0f;
@@ -255,8 +266,10 @@ __device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __
 
 __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
                                                      float2* __restrict__ stage, int stage_cap, WindowDecode& out,
-                                                     const volatile int* progress = nullptr)
+                                                     const volatile int* progress_counter = nullptr, uint64_t* bell = nullptr)
 {
+  ProgressWait pw_{progress_counter, bell, 0u};
+  ProgressWait* const progress = progress_counter ? &pw_ : nullptr;
   const int lane = threadIdx.x & 31;
   const float n = c.n_tag_bit_f;
   const float half = f_div(n, 2.0f);

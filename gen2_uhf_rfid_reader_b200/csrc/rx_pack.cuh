@@ -55,6 +55,7 @@ struct PackArgs {
 struct PackSegCtl {
   uint64_t raw_full[kPRawStages];
   uint64_t win_ready[2], win_free[2];
+  uint64_t bell[2];          // doorbell of the streaming decode: one arrival per progress publication
   int meta_kind[2], meta_open[2], meta_ordinal[2], meta_len[2];
   int progress[2];
   int aborted[2];
@@ -62,6 +63,19 @@ struct PackSegCtl {
   int n_ev[kPS];
   TileEvent ev[kPS][kMaxTileEvents];
 };
+
+#ifdef RFID_B200_PHASE_PROFILE
+// developer aid (tools/pack_profile.py): per-phase clock64() sums of every tile warp / chain warp, written to the window tap
+#define PP_DECL long long pp_t0 = clock64(), pp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long* pp_step_log = nullptr; int pp_step = 0;
+#define PP_MARK(i) { const long long pp_t1 = clock64(); pp_acc[i] += pp_t1 - pp_t0; if (pp_step_log && lane == 0) pp_step_log[pp_step * 8 + (i)] = pp_t1 - pp_t0; pp_t0 = pp_t1; }
+#define PP_SUB(i) { const long long pp_t2 = clock64(); if (pp_step_log && lane == 0) pp_step_log[128 * 8 + pp_step * 8 + (i)] = pp_t2 - pp_t0; }
+#define PP_DUMP(row) if (lane == 0 && A.window_tap) { long long* o = reinterpret_cast<long long*>(A.window_tap) + (size_t)(row) * 8; for (int q_ = 0; q_ < 8; q_++) o[q_] = pp_acc[q_]; }
+#else
+#define PP_DECL
+#define PP_MARK(i)
+#define PP_SUB(i)
+#define PP_DUMP(row)
+#endif
 
 enum : int { PBAR_X = 1, PBAR_Y = 3 };
 template <int BASE>
@@ -110,7 +124,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
   if (threadIdx.x < G) {
     PackSegCtl& c = ctl_all[threadIdx.x];
     for (int s = 0; s < kPRawStages; s++) mbar_init(&c.raw_full[s], 1);
-    for (int s = 0; s < 2; s++) { mbar_init(&c.win_ready[s], 1); mbar_init(&c.win_free[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&c.win_ready[s], 1); mbar_init(&c.win_free[s], 1); mbar_init(&c.bell[s], 1); }
     for (int s = 0; s < kPS; s++) { c.n_e[s] = 0; c.n_ev[s] = 0; }
     mbar_fence_init();
   }
@@ -194,7 +208,15 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     float2 dc_open = make_float2(0.f, 0.f);
     float2* win = win_base;
 
+    PP_DECL
+#ifdef RFID_B200_PHASE_PROFILE
+    if (seg == 0 && A.window_tap) pp_step_log = reinterpret_cast<long long*>(A.window_tap) + (size_t)(A.nseg + gridDim.x) * 8;
+#endif
     for (int i = 0; i < nsteps; i++) {
+#ifdef RFID_B200_PHASE_PROFILE
+      pp_step = i;
+#endif
+      PP_MARK(5)
       // ================================================================= P1(i): matched filter, |y|, ring differences
       if (i < ntiles) {
         const int k = i, ts = k & (kPS - 1);
@@ -202,6 +224,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         const int delta = -odd - (k > 0 ? DECIM - 1 : 0);
         const int nvalid = min(kTT, n_out - k * kTT);
         mbar_wait(&B.raw_full[rs], raw_par);
+        PP_MARK(0)
         const int t0 = Q * lane;
         const int base = DECIM * t0 - (DECIM - 1) - delta;
         float2 w[MFQ - 1 + Q];
@@ -231,8 +254,11 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
             w[MFQ - 1 + h + q] = b;
           }
         }
+        PP_SUB(0)
         __syncwarp();  // raw stage consumed
         if (lane == 0 && k + kPRawStages < ntiles) load_tile(k + kPRawStages, rs);
+        __syncwarp();
+        PP_SUB(1)
         if (++rs == kPRawStages) { rs = 0; raw_par ^= 1u; }
 #pragma unroll
         for (int m = 0; m < MFQ - 1; m++) {
@@ -241,14 +267,22 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           w[m] = lane ? make_float2(ux, uy) : b_keep[m];
           b_keep[m] = make_float2(__shfl_sync(0xffffffffu, mine.x, 31), __shfl_sync(0xffffffffu, mine.y, 31));
         }
+        PP_SUB(2)
         float2 y[Q];
         float a[Q];
+        bool risky = false;
 #pragma unroll
         for (int q = 0; q < Q; q++) {
           y[q] = w[q];
 #pragma unroll
           for (int m = 1; m < MFQ; m++) y[q] = c_add2(y[q], w[q + m]);
-          a[q] = cabsf_ref(y[q].x, y[q].y);  // gate_impl.cc:130
+          bool rq;
+          a[q] = cabsf_quick(y[q].x, y[q].y, rq);  // gate_impl.cc:130
+          risky = risky || rq;
+        }
+        if (__any_sync(0xffffffffu, risky)) {  // rare (about one tile in 60): the exact evaluation for the whole warp
+#pragma unroll
+          for (int q = 0; q < Q; q++) a[q] = cabsf_ref(y[q].x, y[q].y);
         }
         {
           float4* py = reinterpret_cast<float4*>(ring_y + ts * kTT + t0);
@@ -256,6 +290,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           py[1] = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
           *reinterpret_cast<float4*>(ring_a + ts * kTT + t0) = make_float4(a[0], a[1], a[2], a[3]);
         }
+        PP_SUB(3)
         __syncwarp();  // this tile's |y| and y visible to the lookbacks below
         float xd[Q], xr[Q], xi[Q];
         int ia = ts * kTT + t0 - C.win_length, iy = ts * kTT + t0 - C.dc_length;
@@ -288,6 +323,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           mx = fmaxf(fmaxf(mx, fabsf(xd[q])), fmaxf(fabsf(xr[q]), fabsf(xi[q])));
           mn = fminf(fminf(mn, fabsf(xd[q])), fminf(fabsf(xr[q]), fabsf(xi[q])));
         }
+        PP_SUB(4)
         const bool all_ok = C.win_div_fast && C.dc_div_fast && mn >= kDivFastMin && mx <= kDivFastMax;
         float qd[Q], qr[Q], qi[Q];
         if (__all_sync(0xffffffffu, all_ok)) {
@@ -317,11 +353,13 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         *reinterpret_cast<float4*>(bufD(k, 1) + t0) = make_float4(qi[0], qi[1], qi[2], qi[3]);
         __syncwarp();
       }
+      PP_MARK(1)
       pbar_arrive<PBAR_X>(i & 1, bar_count);                 // tile i is ready for the chain warp
       if (i >= 1) pbar_sync<PBAR_Y>((i - 1) & 1, bar_count);  // avg_ampl of tile i-1 and dc_est of tile i-3 are final
+      PP_MARK(2)
 
       // ================================================================= E(i-3): window emission (gate_impl.cc:173,187)
-      if (i >= 3 && i - 3 < ntiles) {
+      if (i >= 3 && i - 3 < ntiles && (f_open || B.n_ev[(i - 3) & (kPS - 1)] != 0)) {  // nothing to emit on most tiles
         const int t = i - 3, ps = t & (kPS - 1);
         const float2* py = ring_y + ps * kTT;
         const float* pe_re = bufD(t, 0);
@@ -339,7 +377,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
               for (int j = lane; j < take; j += 32) win[f_wpos + j] = c_sub(py[pos + j], dc_open);
               __threadfence_block();  // samples first, then the counter the decoder (same CTA) polls
               __syncwarp();
-              if (lane == 0) *(volatile int*)&B.progress[f_slot] = f_wpos + take;
+              if (lane == 0) { *(volatile int*)&B.progress[f_slot] = f_wpos + take; mbar_arrive(&B.bell[f_slot]); }
             }
             f_wpos += take;
             pos = epos;
@@ -382,6 +420,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         __syncwarp();
       }
 
+      PP_MARK(3)
       // ================================================================= P3(i-1): thresholds, state machine, DC list
       if (i >= 1 && i - 1 < ntiles) {
         const int t = i - 1, s = t & (kPS - 1);
@@ -393,10 +432,24 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         float* er = bufD(t, 0);
         float* ei = bufD(t, 1);
         bool list_rebuilt = false;
-        if (!terminated) {
-          // thresholds (gate_impl.cc:136,148,154) as 128-bit masks; a tile wholly inside an open window needs none
+        if (!terminated && gate_open && to_ungate - n_samples > nvalid) {
+          // the whole tile lies inside an open window (gate_impl.cc:182-195): nothing to detect, no DC update
+          n_samples += nvalid;
+          list_rebuilt = true;
+        } else if (!terminated) {
+          // thresholds (gate_impl.cc:136,148,154).  First a one-vote test in the lanes' natural 4-sample groups: while the
+          // signal is high and no sample of the tile falls below its threshold, no edge can occur (carrier only).
           unsigned lt[4] = {0u, 0u, 0u, 0u}, gt[4] = {0u, 0u, 0u, 0u};
-          if (!(gate_open && to_ungate - n_samples > nvalid)) {
+          bool quiet = false;
+          if (sig_pos && !gate_open && nvalid == kTT) {
+            const float4 av = *reinterpret_cast<const float4*>(davg + 4 * lane);
+            const float4 aa = *reinterpret_cast<const float4*>(ta + 4 * lane);
+            const bool below = aa.x < f_mul(av.x, kThreshFraction) || aa.y < f_mul(av.y, kThreshFraction) ||
+                               aa.z < f_mul(av.z, kThreshFraction) || aa.w < f_mul(av.w, kThreshFraction);
+            quiet = !__any_sync(0xffffffffu, below);
+          }
+          bool have_masks = false;
+          auto make_masks = [&]() {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
               const int p = r * 32 + lane;
@@ -414,12 +467,15 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                 gt[r] &= vm;
               }
             }
-          }
+            have_masks = true;
+          };
           int pos = 0;
           while (pos < nvalid) {
             if (!gate_open) {
               const int run_start = pos;
               int p_open = -1;
+              // (the one-vote result only covers a run that starts the tile with the signal high)
+              if (!have_masks && !(quiet && run_start == 0)) make_masks();
               if (sig_pos && (lt[0] | lt[1] | lt[2] | lt[3]) == 0u) {
                 // carrier only (the common case): no falling edge can occur, only the open test remains
                 if (num_pulses > kNumPulsesCommand) {
@@ -512,7 +568,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         if (lane == 0) { B.n_e[s] = n_e; B.n_ev[s] = min(nev, kMaxTileEvents); }
         __syncwarp();
       }
+      PP_MARK(4)
     }
+    if (have) { PP_DUMP(seg) }
     // ---- end of the segment
     if (have) {
       if (f_open && f_store && lane == 0) {
@@ -520,6 +578,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         *(volatile int*)&B.aborted[f_slot] = 1;
         __threadfence_block();
         *(volatile int*)&B.progress[f_slot] = 1 << 30;
+        mbar_arrive(&B.bell[f_slot]);
       }
       __syncwarp();
       if (lane == 0) A.counts[seg] = wcount;
@@ -538,24 +597,35 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     int n_out = 0;
     if (active) n_out = (int)(A.segs[seg0 + g].length / DECIM);
     float acc = 0.f;
+    PP_DECL
+#ifdef RFID_B200_PHASE_PROFILE
+    if (blockIdx.x == 0 && A.window_tap) pp_step_log = reinterpret_cast<long long*>(A.window_tap) + (size_t)(A.nseg + gridDim.x) * 8 + 64 * 8;
+#endif
     for (int i = 0; i < nsteps; i++) {
+#ifdef RFID_B200_PHASE_PROFILE
+      pp_step = i;
+#endif
       pbar_sync<PBAR_X>(i & 1, bar_count);
-      if (active) {
-        int n = 0;
-        float* buf = dA;
-        if (comp == 0) {
-          n = min(kTT, max(0, n_out - i * kTT));
-          buf = dA + (size_t)((i & 1) * G + g) * kPChainBuf;
-        } else if (i >= 2) {
-          const int t = i - 2;
-          n = ctl_all[g].n_e[t & (kPS - 1)];
-          buf = dD + (size_t)(((t & (kPS - 1)) * 2 + (comp - 1)) * G + g) * kPChainBuf;
-        }
-        chain_inplace(buf, (n + 15) & ~15, acc);
+      PP_MARK(0)
+      {
+        // branch-free selection of this lane's buffer and length, then ONE convergent loop for all 24 chains
+        const int t = i - 2;
+        const int n_avg = min(kTT, max(0, n_out - i * kTT));
+        const int n_dc = (active && comp > 0 && i >= 2) ? ctl_all[g].n_e[t & (kPS - 1)] : 0;
+        const int n = active ? (comp == 0 ? n_avg : n_dc) : 0;
+        const int ofsA = ((i & 1) * G + g) * kPChainBuf;
+        const int ofsD = (((t & (kPS - 1)) * 2 + (comp - 1)) * G + g) * kPChainBuf;
+        float* buf = comp == 0 ? dA + ofsA : dD + (active && comp > 0 ? ofsD : 0);
+        const int n16 = (n + 15) & ~15;
+        __syncwarp();
+        chain_inplace(buf, n16, acc);
       }
       __syncwarp();
+      PP_MARK(1)
       if (i + 1 < nsteps) pbar_arrive<PBAR_Y>(i & 1, bar_count);
+      PP_MARK(2)
     }
+    PP_DUMP(A.nseg + blockIdx.x)
   } else {
     // ======================================================================================= decoder warp
     const int g = warp - G - 1;
@@ -572,14 +642,16 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         const int ordinal = B.meta_ordinal[j & 1], open_idx = B.meta_open[j & 1], len = B.meta_len[j & 1];
         const float2* win = win_base + (kind ? A.rn16_pad : 0);
         WindowDecode wd;
-        decode_window_staged(C, kind, win, len, dstage, A.dstage_samples, wd, (const volatile int*)&B.progress[j & 1]);
+        decode_window_staged(C, kind, win, len, dstage, A.dstage_samples, wd, (const volatile int*)&B.progress[j & 1], &B.bell[j & 1]);
         rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
         const bool aborted = *(volatile int*)&B.aborted[j & 1] != 0;
         if (lane == 0 && !aborted) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
+#ifndef RFID_B200_PHASE_PROFILE
         if (A.window_tap) {
           float2* tap = A.window_tap + ((size_t)seg * A.max_windows + ordinal) * C.len_epc;
           for (int p = lane; p < len; p += 32) tap[p] = __ldcg(win + p);
         }
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive(&B.win_free[j & 1]);
       }
