@@ -35,6 +35,7 @@ struct rfid_b200_ctx {
   bool timing;
   cudaEvent_t ev0, ev1;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<cudaEvent_t> ev_pool;  // timing events are created once and reused (no driver calls inside a timed loop)
   float kernel_ms;
   int kernel_launches;
   int sm_count;
@@ -259,8 +260,8 @@ void drain_timing(rfid_b200_ctx* ctx)
       ctx->kernel_ms += ms;
       ctx->kernel_launches++;
     }
-    cudaEventDestroy(pr.first);
-    cudaEventDestroy(pr.second);
+    ctx->ev_pool.push_back(pr.first);
+    ctx->ev_pool.push_back(pr.second);
   }
   ctx->pending.clear();
 }
@@ -372,6 +373,8 @@ void rfid_b200_destroy(rfid_b200_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   drain_timing(ctx);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  ctx->ev_pool.clear();
   void* ptrs[] = {ctx->d_win, ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
                   ctx->d_gate, ctx->d_gate_out, ctx->d_one, ctx->d_mask, ctx->d_chunk, ctx->d_bursts, ctx->d_ing,
                   ctx->d_script, ctx->d_sim_res, ctx->d_sim_cnt};
@@ -404,6 +407,14 @@ int rfid_b200_enable_kernel_timing(rfid_b200_ctx* ctx, int on)
 {
   if (!ctx) return RFID_B200_EINVAL;
   ctx->timing = on != 0;
+  if (ctx->timing) {
+    cudaSetDevice(ctx->device);
+    while (ctx->ev_pool.size() < 128) {  // enough for 64 launches in flight before the first drain
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); break; }
+      ctx->ev_pool.push_back(e);
+    }
+  }
   return RFID_B200_OK;
 }
 
@@ -451,8 +462,10 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
   A.cfg = ctx->cfg;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->timing) {
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    for (cudaEvent_t* pe : {&e0, &e1}) {
+      if (!ctx->ev_pool.empty()) { *pe = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+      else CK(cudaEventCreate(pe));
+    }
     CK(cudaEventRecord(e0, s));
   }
   if (pack_ok(ctx->cfg) && !ctx->pack_disabled) {
@@ -462,7 +475,7 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
     P.iq = A.iq; P.n_raw = A.n_raw; P.segs = A.segs; P.nseg = nseg; P.max_windows = A.max_windows;
     P.results = A.results; P.counts = A.counts; P.window_tap = A.window_tap; P.win_scratch = A.win_scratch;
     P.cfg = ctx->cfg;
-    rx_pack_kernel<5, 5><<<(nseg + P.G - 1) / P.G, 32 * (2 * P.G + 1), P.smem_bytes, s>>>(P);
+    rx_pack_kernel<5, 5><<<(nseg + P.G - 1) / P.G, 32 * (3 * P.G + 2), P.smem_bytes, s>>>(P);
   } else {
     fn<<<nseg, fast_path_ok(ctx->cfg) ? kSplitThreads : kFusedThreads, A.smem_bytes, s>>>(A);
   }
@@ -510,11 +523,15 @@ int rfid_b200_reduce_stats(const rfid_b200_ctx* ctx, const rfid_b200_window_resu
   memset(out, 0, sizeof(*out));
   const int max_slot = 1 << ctx->cfg.fixed_q;
   out->max_slot_number = max_slot;
-  std::map<int, int> tag_reads;
+  std::map<int, int> tag_reads;   // what print_results() reports
+  std::map<int, int> seg_reads;   // non-continuous mode: the tag_reads of the segment's own (fresh) reader_state
   int round = 1, slot = 1, nq = 1, total_q = 0;
   bool stopped = false;
   for (int s = 0; s < nseg; s++) {
-    if (!continuous) { round = 1; slot = 1; nq = 1; stopped = false; }
+    // an independent segment = a reference run with freshly constructed blocks: counters AND the unique-tag stop rule
+    // (gate_impl.cc:101-104) start over; the global map only accumulates for reporting
+    if (!continuous) { round = 1; slot = 1; nq = 1; stopped = false; seg_reads.clear(); }
+    std::map<int, int>& rule_reads = continuous ? tag_reads : seg_reads;
     const int n = counts[s] < max_per_seg ? counts[s] : max_per_seg;
     const rfid_b200_window_result* r = recs + (size_t)s * max_per_seg;
     for (int k = 0; k < n && !stopped; k++) {
@@ -528,13 +545,17 @@ int rfid_b200_reduce_stats(const rfid_b200_ctx* ctx, const rfid_b200_window_resu
       } else {
         slot++;
         if (slot > max_slot) { slot = 1; round++; }
-        if (r[k].crc_ok == 1) { out->n_epc_correct++; tag_reads[r[k].tag_id]++; }
+        if (r[k].crc_ok == 1) {
+          out->n_epc_correct++;
+          tag_reads[r[k].tag_id]++;
+          if (!continuous) seg_reads[r[k].tag_id]++;
+        }
         next_query = true;
       }
       out->n_windows++;
       if (next_query) {
         nq++;
-        if (nq > ctx->cfg.max_queries || (int)tag_reads.size() > ctx->cfg.max_tags) stopped = true;
+        if (nq > ctx->cfg.max_queries || (int)rule_reads.size() > ctx->cfg.max_tags) stopped = true;
       }
     }
     if (!continuous) total_q += nq;

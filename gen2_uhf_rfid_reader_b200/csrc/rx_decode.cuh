@@ -234,7 +234,7 @@ __device__ __forceinline__ void progress_wait(ProgressWait* pw, int need)
     if (pw->bell) { if (mbar_try_wait_hint(pw->bell, pw->seen & 1u, 2000)) pw->seen++; }
     else __nanosleep(RFID_B200_PROGRESS_NS);
   }
-  __threadfence_block();  // the samples were written (and fenced, CTA scope) before the counter moved
+  asm volatile("fence.acq_rel.cta;" ::: "memory");  // the samples were written (and fenced, CTA scope) before the counter moved
 }
 
 __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail,

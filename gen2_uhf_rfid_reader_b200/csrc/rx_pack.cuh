@@ -28,8 +28,12 @@ constexpr int kPS = 4;                       // tiles in the time ring (tile i, 
 constexpr int kPRing = kPS * kTT;
 constexpr int kPRawStages = 3;
 constexpr int kPMaxSeg = 7;                  // segments per CTA (chain lanes 8*c + g, g < 8)
+#ifndef RFID_B200_CHAIN_WARP_OFS
+#define RFID_B200_CHAIN_WARP_OFS 1
+#endif
+constexpr int kChainWarpOfs = RFID_B200_CHAIN_WARP_OFS;   // chain warp = 2G + this, loader = 2G + (1 - this): picks the chain's SM sub-partition
 constexpr int kPChainBuf = kTT + 12;         // floats per running-sum buffer: read-ahead pad; 560 B = 48 mod 128
-constexpr int kPackMaxThreads = 32 * (2 * kPMaxSeg + 1);
+constexpr int kPackMaxThreads = 32 * (3 * kPMaxSeg + 2);
 
 struct PackArgs {
   const float2* iq;
@@ -54,11 +58,10 @@ struct PackArgs {
 
 struct PackSegCtl {
   uint64_t raw_full[kPRawStages];
-  uint64_t win_ready[2], win_free[2];
-  uint64_t bell[2];          // doorbell of the streaming decode: one arrival per progress publication
-  int meta_kind[2], meta_open[2], meta_ordinal[2], meta_len[2];
-  int progress[2];
-  int aborted[2];
+  uint64_t raw_empty[kPRawStages];  // warp A (1 arrival) -> loader warp
+  uint64_t go, done;         // warp B -> warp C: "emit tile go_tile" / warp C -> warp B: "copied, the ring slot may go"
+  int go_tile;               // tile to emit; -1: the segment is over
+  int emit[kPS];             // does tile t (slot t & 3) contain window samples or gate events?  (written by P3)
   int n_e[kPS];
   int n_ev[kPS];
   TileEvent ev[kPS][kMaxTileEvents];
@@ -66,30 +69,265 @@ struct PackSegCtl {
 
 #ifdef RFID_B200_PHASE_PROFILE
 // developer aid (tools/pack_profile.py): per-phase clock64() sums of every tile warp / chain warp, written to the window tap
-#define PP_DECL long long pp_t0 = clock64(), pp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long* pp_step_log = nullptr; int pp_step = 0;
-#define PP_MARK(i) { const long long pp_t1 = clock64(); pp_acc[i] += pp_t1 - pp_t0; if (pp_step_log && lane == 0) pp_step_log[pp_step * 8 + (i)] = pp_t1 - pp_t0; pp_t0 = pp_t1; }
+#define PP_DECL long long pp_t0 = clock64(), pp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long* pp_step_log = nullptr; long long* pp_abs_log = nullptr; int pp_step = 0;
+#define PP_MARK(i) { const long long pp_t1 = clock64(); pp_acc[i] += pp_t1 - pp_t0; if (pp_step_log && lane == 0) { pp_step_log[pp_step * 8 + (i)] = pp_t1 - pp_t0; if (pp_abs_log) pp_abs_log[pp_step * 8 + (i)] = pp_t1 - pp_cta_t0; } pp_t0 = pp_t1; }
 #define PP_SUB(i) { const long long pp_t2 = clock64(); if (pp_step_log && lane == 0) pp_step_log[128 * 8 + pp_step * 8 + (i)] = pp_t2 - pp_t0; }
+#define PP_SUBB(i) { const long long pp_t2 = clock64(); if (pp_step_log && lane == 0) pp_step_log[64 * 8 + pp_step * 8 + (i)] = pp_t2 - pp_t0; }
 #define PP_DUMP(row) if (lane == 0 && A.window_tap) { long long* o = reinterpret_cast<long long*>(A.window_tap) + (size_t)(row) * 8; for (int q_ = 0; q_ < 8; q_++) o[q_] = pp_acc[q_]; }
 #else
 #define PP_DECL
 #define PP_MARK(i)
 #define PP_SUB(i)
+#define PP_SUBB(i)
 #define PP_DUMP(row)
 #endif
 
-enum : int { PBAR_X = 1, PBAR_Y = 3 };
+// release / acquire fence at CTA scope (fence.sc, which __threadfence_block() emits, is far more expensive and not needed:
+// the window hand-off is a plain producer -> consumer edge)
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+#ifdef RFID_B200_EXP_RELAXED_ARRIVE
+#define MBAR_ARRIVE_EXP mbar_arrive_relaxed
+#else
+#define MBAR_ARRIVE_EXP mbar_arrive
+#endif
+enum : int { PBAR_X = 1, PBAR_Y = 3, PBAR_PAIR = 5 };  // + segment slot: warps A and B of one segment
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 template <int BASE>
 __device__ __forceinline__ void pbar_sync(int parity, int count)
 {
   if (parity == 0) asm volatile("bar.sync %0, %1;" ::"n"((int)BASE), "r"(count) : "memory");
   else asm volatile("bar.sync %0, %1;" ::"n"((int)(BASE + 1)), "r"(count) : "memory");
 }
+// (bar.arrive / bar.sync order the executing thread's prior shared-memory accesses for the threads that complete the
+// barrier -- the PTX producer/consumer pattern; no separate fence, which would cost a MEMBAR.SC on the critical path)
 template <int BASE>
 __device__ __forceinline__ void pbar_arrive(int parity, int count)
 {
-  __threadfence_block();
   if (parity == 0) asm volatile("bar.arrive %0, %1;" ::"n"((int)BASE), "r"(count) : "memory");
   else asm volatile("bar.arrive %0, %1;" ::"n"((int)(BASE + 1)), "r"(count) : "memory");
+}
+
+
+// ---- the edge / pulse state machine of one closed run as pure 128-bit mask arithmetic -------------------------------
+// Same decisions as fsm_closed_run (rx_fused_split.cuh) and therefore as the reference's sample loop
+// (gate_impl.cc:145-180), but without per-edge work: every quantity below is warp-uniform, computed redundantly by all
+// lanes from the two 128-bit threshold masks -- no shuffles, no ballots, no find-nth-set-bit.
+//   states     carry chain (state' = rise | keep & state), as before
+//   pulses     a rise at p is a valid pulse when the fall before it is more than half_pw back: no fall bit at p-1 .. p-half_pw
+//   num_pulses valid rises since the last invalid one (plus the carried count while no invalid rise has occurred)
+//   opening    the carried state reaches T1 before the first edge, or a rise r with num_pulses > 5 is followed by
+//              n_T1 + 1 edge-free samples inside the tile (gate opens at r + 1 + n_T1; a fall there wins)
+__device__ __forceinline__ unsigned m_below(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)); }
+__device__ __forceinline__ int m_ffs128(const unsigned* a)
+{
+  const unsigned long long lo = a[0] | ((unsigned long long)a[1] << 32), hi = a[2] | ((unsigned long long)a[3] << 32);
+  return lo ? __ffsll((long long)lo) - 1 : (hi ? 63 + __ffsll((long long)hi) : 128);
+}
+__device__ __forceinline__ int m_fls128(const unsigned* a)
+{
+  const unsigned long long lo = a[0] | ((unsigned long long)a[1] << 32), hi = a[2] | ((unsigned long long)a[3] << 32);
+  return hi ? 127 - __clzll((long long)hi) : (lo ? 63 - __clzll((long long)lo) : -1);
+}
+// number of set bits of a[] at positions [lo, hi)
+__device__ __forceinline__ int m_popc_range(const unsigned* a, int lo, int hi)
+{
+  int n = 0;
+#pragma unroll
+  for (int w = 0; w < 4; w++) n += __popc(a[w] & m_below(hi - 32 * w) & ~m_below(lo - 32 * w));
+  return n;
+}
+__device__ __forceinline__ bool m_any_range(const unsigned* a, int lo, int hi)
+{
+  unsigned v = 0;
+#pragma unroll
+  for (int w = 0; w < 4; w++) v |= a[w] & m_below(hi - 32 * w) & ~m_below(lo - 32 * w);
+  return v != 0u;
+}
+// single-bit helpers with static word indices (a dynamically indexed register array would be demoted to local memory)
+__device__ __forceinline__ unsigned m_word_bit(int p, int w) { return (p >> 5) == w ? (1u << (p & 31)) : 0u; }
+__device__ __forceinline__ bool m_bit(const unsigned* a, int p)
+{
+  return ((a[0] & m_word_bit(p, 0)) | (a[1] & m_word_bit(p, 1)) | (a[2] & m_word_bit(p, 2)) | (a[3] & m_word_bit(p, 3))) != 0u;
+}
+__device__ __forceinline__ void m_clear(unsigned* a, int p)
+{
+#pragma unroll
+  for (int w = 0; w < 4; w++) a[w] &= ~m_word_bit(p, w);
+}
+
+__device__ __forceinline__ int fsm_closed_run_masks(const Mask128& lt, const Mask128& gt, int from, int nvalid, int n_T1,
+                                                    int half_pw, GateFsm& st)
+{
+  unsigned F[4], R[4], X[4], RS[4], FE[4], E[4];
+  unsigned carry = st.sig_pos ? 1u : 0u;
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    const unsigned live = ~m_below(from - 32 * w);
+    F[w] = lt.w[w] & live;
+    R[w] = gt.w[w] & live;
+    const unsigned Pk = ~(F[w] | R[w]);
+    const unsigned long long sum = (unsigned long long)(R[w] | Pk) + R[w] + carry;
+    X[w] = Pk ^ (unsigned)sum;  // carry INTO each bit = state before that position
+    carry = (unsigned)(sum >> 32);
+    RS[w] = ~X[w] & R[w];
+    FE[w] = X[w] & F[w];
+    E[w] = RS[w] | FE[w];
+  }
+  const int e_first = m_ffs128(E);
+  const int first_edge = e_first < nvalid ? e_first : nvalid;
+  // ---- the carried state reaches T1 before anything happens
+  if (st.sig_pos && st.num_pulses > kNumPulsesCommand) {
+    const int p_open = from + max(0, n_T1 - st.n_samples);
+    if (p_open < first_edge && p_open < nvalid) {
+      st.sig_pos = true; st.num_pulses = 0; st.n_samples = 1;
+      return p_open;
+    }
+  }
+  if (e_first >= nvalid) { st.n_samples += nvalid - from; return -1; }
+  // ---- valid / invalid pulses
+  unsigned VR[4], IR[4];
+#pragma unroll
+  for (int w = 0; w < 4; w++) VR[w] = RS[w];
+  {
+    unsigned S[4] = {FE[0], FE[1], FE[2], FE[3]};
+    for (int k = 0; k < half_pw; k++) {  // fall bits moved up by k+1 positions knock the rises they reach out
+      const unsigned s3 = (S[3] << 1) | (S[2] >> 31), s2 = (S[2] << 1) | (S[1] >> 31), s1 = (S[1] << 1) | (S[0] >> 31), s0 = S[0] << 1;
+      S[0] = s0; S[1] = s1; S[2] = s2; S[3] = s3;
+#pragma unroll
+      for (int w = 0; w < 4; w++) VR[w] &= ~S[w];
+    }
+  }
+  if (m_bit(RS, e_first)) {
+    // the tile's first edge is a rise: its pulse began before the run (n_samples carried in)
+    const bool valid = st.n_samples + (e_first - from + 1) > half_pw;
+    if (!valid) m_clear(VR, e_first);
+  }
+#pragma unroll
+  for (int w = 0; w < 4; w++) IR[w] = RS[w] & ~VR[w];
+  const int np_in = st.num_pulses;
+  auto np_at = [&](int r) {  // num_pulses right after the rise at r
+    unsigned res[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) res[w] = IR[w] & m_below(r + 1 - 32 * w);
+    const int last = m_fls128(res);
+    return last >= 0 ? m_popc_range(VR, last + 1, r + 1) : np_in + m_popc_range(VR, 0, r + 1);
+  };
+  // ---- a rise followed by n_T1 + 1 quiet samples inside the tile
+  const int lim = nvalid - 1 - n_T1;  // rises at or above lim cannot open the gate within this tile
+  if (lim > 0) {
+    unsigned cand[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) cand[w] = RS[w] & m_below(lim - 32 * w);
+    if (lim <= n_T1 + 1) {
+      // (any earlier rise below lim is followed by a fall within its T1: only the last one can qualify)
+      const int r = m_fls128(cand);
+#pragma unroll
+      for (int w = 0; w < 4; w++) cand[w] = r >= 0 ? m_word_bit(r, w) : 0u;
+    }
+    while ((cand[0] | cand[1] | cand[2] | cand[3]) != 0u) {
+      const int r = m_ffs128(cand);
+      m_clear(cand, r);
+      if (!m_any_range(E, r + 1, r + 2 + n_T1) && np_at(r) > kNumPulsesCommand) {
+        st.sig_pos = true; st.num_pulses = 0; st.n_samples = 1;
+        return r + 1 + n_T1;
+      }
+    }
+  }
+  // ---- no opening: state after the last edge
+  const int e_last = m_fls128(E);
+  st.sig_pos = m_bit(RS, e_last);
+  st.n_samples = nvalid - 1 - e_last;
+  const int r_last = m_fls128(RS);
+  if (r_last >= 0) st.num_pulses = np_at(r_last);
+  return -1;
+}
+
+
+// ---- the same state machine with the four mask words spread over lanes 0..3 ---------------------------------------
+// fsm_closed_run_masks walks every 128-bit quantity as four dependent 32-bit words in every lane: ~400 dependent scalar
+// instructions, i.e. a couple of thousand cycles of latency for one warp.  Here lane w (w < 4) owns word w; positions and
+// counts are combined with redux.sync / vote (one instruction each), the carry chain across the words by carry look-ahead
+// (both sums per word, a 3-step select on two ballots).  Identical decisions; same arguments and result.
+__device__ __forceinline__ int fsm_closed_run_lanes(const Mask128& lt, const Mask128& gt, int from, int nvalid, int n_T1,
+                                                    int half_pw, GateFsm& st)
+{
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int w = lane & 3;
+  const bool own = lane < 4;
+  const int base = 32 * w;
+  const unsigned ltw = w == 0 ? lt.w[0] : (w == 1 ? lt.w[1] : (w == 2 ? lt.w[2] : lt.w[3]));
+  const unsigned gtw = w == 0 ? gt.w[0] : (w == 1 ? gt.w[1] : (w == 2 ? gt.w[2] : gt.w[3]));
+  const unsigned live = ~m_below(from - base);
+  const unsigned F = ltw & live, R = gtw & live;
+  const unsigned Pk = ~(F | R);
+  // carry look-ahead over the four words
+  const unsigned long long sum0 = (unsigned long long)(R | Pk) + R, sum1 = sum0 + 1ull;
+  const unsigned C0 = __ballot_sync(FULL, own && (sum0 >> 32) != 0ull), C1 = __ballot_sync(FULL, own && (sum1 >> 32) != 0ull);
+  const unsigned cin0 = st.sig_pos ? 1u : 0u;
+  const unsigned cin1 = cin0 ? (C1 & 1u) : (C0 & 1u);
+  const unsigned cin2 = cin1 ? ((C1 >> 1) & 1u) : ((C0 >> 1) & 1u);
+  const unsigned cin3 = cin2 ? ((C1 >> 2) & 1u) : ((C0 >> 2) & 1u);
+  const unsigned cin = w == 0 ? cin0 : (w == 1 ? cin1 : (w == 2 ? cin2 : cin3));
+  const unsigned X = Pk ^ (unsigned)(cin ? sum1 : sum0);   // state before each position
+  const unsigned RS = ~X & R, FE = X & F, E = RS | FE;
+  auto first_of = [&](unsigned m) { return __reduce_min_sync(FULL, (own && m) ? base + __ffs(m) - 1 : 128); };
+  auto last_of = [&](unsigned m) { return __reduce_max_sync(FULL, (own && m) ? base + 31 - __clz(m) : -1); };
+  auto bit_at = [&](unsigned m, int p) { return __any_sync(FULL, own && (p >> 5) == w && ((m >> (p & 31)) & 1u)); };
+  const int e_first = first_of(E);
+  const int first_edge = e_first < nvalid ? e_first : nvalid;
+  if (st.sig_pos && st.num_pulses > kNumPulsesCommand) {
+    const int p_open = from + max(0, n_T1 - st.n_samples);
+    if (p_open < first_edge && p_open < nvalid) {
+      st.sig_pos = true; st.num_pulses = 0; st.n_samples = 1;
+      return p_open;
+    }
+  }
+  if (e_first >= nvalid) { st.n_samples += nvalid - from; return -1; }
+  // valid pulses: no fall within the half_pw positions before the rise
+  const unsigned fe_prev = __shfl_up_sync(FULL, FE, 1);
+  const unsigned fe_lo = w == 0 ? 0u : fe_prev;
+  unsigned knock = 0u;
+  for (int k = 1; k <= half_pw; k++) knock |= (FE << k) | (fe_lo >> (32 - k));
+  unsigned VR = RS & ~knock;
+  if (bit_at(RS, e_first)) {
+    const bool valid = st.n_samples + (e_first - from + 1) > half_pw;   // the pulse began before the run
+    if (!valid && (e_first >> 5) == w) VR &= ~(1u << (e_first & 31));
+  }
+  const unsigned IR = RS & ~VR;
+  const int np_in = st.num_pulses;
+  auto np_at = [&](int r) {
+    const unsigned upto = m_below(r + 1 - base);
+    const int last = last_of(IR & upto);
+    const unsigned rng = upto & ~m_below(last + 1 - base);
+    const int cnt = __reduce_add_sync(FULL, own ? __popc(VR & rng) : 0);
+    return last >= 0 ? cnt : np_in + cnt;
+  };
+  const int lim = nvalid - 1 - n_T1;
+  if (lim > 0) {
+    unsigned cand = RS & m_below(lim - base);
+    if (lim <= n_T1 + 1) {
+      const int r = last_of(cand);
+      cand = (r >= 0 && (r >> 5) == w) ? (1u << (r & 31)) : 0u;
+    }
+    while (true) {
+      const int r = first_of(cand);
+      if (r >= 128) break;
+      if ((r >> 5) == w) cand &= ~(1u << (r & 31));
+      const unsigned quiet_rng = m_below(r + 2 + n_T1 - base) & ~m_below(r + 1 - base);
+      if (!__any_sync(FULL, own && (E & quiet_rng) != 0u) && np_at(r) > kNumPulsesCommand) {
+        st.sig_pos = true; st.num_pulses = 0; st.n_samples = 1;
+        return r + 1 + n_T1;
+      }
+    }
+  }
+  const int e_last = last_of(E);
+  st.sig_pos = bit_at(RS, e_last);
+  st.n_samples = nvalid - 1 - e_last;
+  const int r_last = last_of(RS);
+  if (r_last >= 0) st.num_pulses = np_at(r_last);
+  return -1;
 }
 
 template <int DECIM, int MFQ>
@@ -97,6 +335,10 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
 {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ PackSegCtl ctl_all[kPMaxSeg];
+#ifdef RFID_B200_PHASE_PROFILE
+  __shared__ long long pp_cta_t0;
+  if (threadIdx.x == 0) pp_cta_t0 = clock64();
+#endif
 
   static_assert(MFQ >= 2, "pack kernel: block-sum matched filter");
   constexpr int Q = kTT / 32;
@@ -123,9 +365,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
   }
   if (threadIdx.x < G) {
     PackSegCtl& c = ctl_all[threadIdx.x];
-    for (int s = 0; s < kPRawStages; s++) mbar_init(&c.raw_full[s], 1);
-    for (int s = 0; s < 2; s++) { mbar_init(&c.win_ready[s], 1); mbar_init(&c.win_free[s], 1); mbar_init(&c.bell[s], 1); }
-    for (int s = 0; s < kPS; s++) { c.n_e[s] = 0; c.n_ev[s] = 0; }
+    for (int s = 0; s < kPRawStages; s++) { mbar_init(&c.raw_full[s], 1); mbar_init(&c.raw_empty[s], 1); }
+    mbar_init(&c.go, 1); mbar_init(&c.done, 1);
+    for (int s = 0; s < kPS; s++) { c.n_e[s] = 0; c.n_ev[s] = 0; c.emit[s] = 0; }
     mbar_fence_init();
   }
   // lockstep length: the longest segment of the CTA
@@ -137,9 +379,10 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
   const int nsteps = max_tiles + 3;
   __syncthreads();
 
-  if (warp < G) {
-    // ======================================================================================= tile warp
-    const int g = warp;
+  if (warp < 2 * G) {
+    // ======================================================================================= tile warps A (P1) and B (E, P3)
+    const bool is_a = warp < G;
+    const int g = is_a ? warp : warp - G;
     const bool have = g < g_act;
     const int seg = seg0 + g;
     rfid_b200_segment sg;
@@ -157,60 +400,22 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     auto bufA = [&](int tile) { return dA + (size_t)((tile & 1) * G + g) * kPChainBuf; };
     auto bufD = [&](int tile, int comp) { return dD + (size_t)(((tile & (kPS - 1)) * 2 + comp) * G + g) * kPChainBuf; };
 
-    // ---- P1 state: raw tile geometry (as rx_fused_split.cuh)
     const int odd = (int)(sg.offset & 1ull);
-    const uint32_t fast_bytes = (uint32_t)((DECIM * kTT + 2 * odd) * 8);
-    int fast_tiles = 0;
-    {
-      const long long by_len = ((long long)sg.length - 1 - (long long)DECIM * (kTT - 1)) / ((long long)DECIM * kTT);
-      const long long room = (long long)A.n_raw - (long long)sg.offset + (DECIM - 1) + odd - (DECIM * kTT + 2 * odd);
-      const long long by_buf = room >= 0 ? room / ((long long)DECIM * kTT) : -1;
-      long long f = (by_len < by_buf ? by_len : by_buf) + 1;
-      if (sg.length < (unsigned)(DECIM * kTT)) f = 0;
-      fast_tiles = f < 0 ? 0 : (f > ntiles ? ntiles : (int)f);
-    }
-    const float2* const fast_src = A.iq + sg.offset - (DECIM - 1) - odd;
-    FusedArgs FA;  // issue_tile_load only reads iq / n_raw
-    FA.iq = A.iq; FA.n_raw = A.n_raw;
-    auto load_tile = [&](int k, int rs_) {
-      float2* dst = raw + (size_t)rs_ * A.raw_stage_samples;
-      if (k >= 1 && k < fast_tiles) {
-        mbar_arrive_expect_tx(&B.raw_full[rs_], fast_bytes);
-        tma_load_1d(dst, fast_src + (size_t)k * (DECIM * kTT), fast_bytes, &B.raw_full[rs_]);
-      } else {
-        issue_tile_load<DECIM>(FA, sg, k, dst, &B.raw_full[rs_]);
-      }
-    };
-    if (lane == 0)
-      for (int k = 0; k < kPRawStages && k < ntiles; k++) load_tile(k, k);
-    const float winlen_f = (float)C.win_length, dclen_f = (float)C.dc_length;
+    const float dclen_f = (float)C.dc_length;
+    const int pair_bar = PBAR_PAIR + g;
+
+    if (is_a) {
+      // ------------------------------------------------------------------------------------- warp A: P1
+    const float winlen_f = (float)C.win_length;
     float2 b_keep[MFQ - 1];
 #pragma unroll
     for (int m = 0; m < MFQ - 1; m++) b_keep[m] = make_float2(0.f, 0.f);
     int rs = 0;
     uint32_t raw_par = 0;
 
-    // ---- P3 state: the gate (gate_impl.cc:45, global_vars.cc:47, reader_impl.cc:259,262)
-    bool sig_pos = false;
-    int n_samples = 0, num_pulses = 0;
-    bool gate_open = false;
-    int to_ungate = C.len_rn16;
-    int wcount = 0, open_idx = 0;
-    bool cur_store = false;
-    int nq = 1;
-    bool terminated = false;
-    int closed_since = C.dc_length;
-    const int half_pw = C.n_PW / 2;
-
-    // ---- E state: window emission, three tiles behind P1
-    bool f_open = false, f_store = false;
-    int f_wpos = 0, n_signalled = 0, n_freed = 0, f_slot = 0, wsig_ordinal = 0;
-    float2 dc_open = make_float2(0.f, 0.f);
-    float2* win = win_base;
-
     PP_DECL
 #ifdef RFID_B200_PHASE_PROFILE
-    if (seg == 0 && A.window_tap) pp_step_log = reinterpret_cast<long long*>(A.window_tap) + (size_t)(A.nseg + gridDim.x) * 8;
+    if (seg == 0 && A.window_tap) { pp_step_log = reinterpret_cast<long long*>(A.window_tap) + (size_t)(A.nseg + gridDim.x) * 8; pp_abs_log = pp_step_log + 320 * 8; }
 #endif
     for (int i = 0; i < nsteps; i++) {
 #ifdef RFID_B200_PHASE_PROFILE
@@ -254,11 +459,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
             w[MFQ - 1 + h + q] = b;
           }
         }
-        PP_SUB(0)
         __syncwarp();  // raw stage consumed
-        if (lane == 0 && k + kPRawStages < ntiles) load_tile(k + kPRawStages, rs);
-        __syncwarp();
-        PP_SUB(1)
+        if (lane == 0) MBAR_ARRIVE_EXP(&B.raw_empty[rs]);
+        PP_SUB(0)
         if (++rs == kPRawStages) { rs = 0; raw_par ^= 1u; }
 #pragma unroll
         for (int m = 0; m < MFQ - 1; m++) {
@@ -354,77 +557,47 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         __syncwarp();
       }
       PP_MARK(1)
-      pbar_arrive<PBAR_X>(i & 1, bar_count);                 // tile i is ready for the chain warp
+      pbar_arrive<PBAR_X>(i & 1, bar_count);   // tile i is ready for the chain warp
+      pair_sync(pair_bar);                      // warp B is done with step i: ring slot, sum buffers of tile i+1 are free
+    }
+    if (have) { PP_DUMP(seg) }
+    } else {
+      // ------------------------------------------------------------------------------------- warp B: TMA issue, E, P3
+    // ---- P3 state: the gate (gate_impl.cc:45, global_vars.cc:47, reader_impl.cc:259,262)
+    bool sig_pos = false;
+    int n_samples = 0, num_pulses = 0;
+    bool gate_open = false;
+    int to_ungate = C.len_rn16;
+    int wcount = 0, open_idx = 0;
+    bool cur_store = false;
+    int nq = 1;
+    bool terminated = false;
+    int closed_since = C.dc_length;
+    const int half_pw = C.n_PW / 2;
+
+    uint32_t go_count = 0;      // emission requests sent to warp C so far (phase parity of the done barrier)
+
+    PP_DECL
+#ifdef RFID_B200_PHASE_PROFILE
+    if (seg == 0 && A.window_tap) { pp_step_log = reinterpret_cast<long long*>(A.window_tap) + (size_t)(A.nseg + gridDim.x) * 8 + 192 * 8; pp_abs_log = pp_step_log + (384 - 192) * 8; }
+#endif
+    for (int i = 0; i < nsteps; i++) {
+#ifdef RFID_B200_PHASE_PROFILE
+      pp_step = i;
+#endif
+      PP_MARK(5)
+      PP_MARK(0)
       if (i >= 1) pbar_sync<PBAR_Y>((i - 1) & 1, bar_count);  // avg_ampl of tile i-1 and dc_est of tile i-3 are final
       PP_MARK(2)
-
-      // ================================================================= E(i-3): window emission (gate_impl.cc:173,187)
-      if (i >= 3 && i - 3 < ntiles && (f_open || B.n_ev[(i - 3) & (kPS - 1)] != 0)) {  // nothing to emit on most tiles
-        const int t = i - 3, ps = t & (kPS - 1);
-        const float2* py = ring_y + ps * kTT;
-        const float* pe_re = bufD(t, 0);
-        const float* pe_im = bufD(t, 1);
-        const int pvalid = min(kTT, n_out - t * kTT);
-        const int pnev = B.n_ev[ps];
-        int pos = 0;
-        for (int e = 0; e <= pnev; e++) {
-          const bool last = e == pnev;
-          const int etype = last ? 0 : B.ev[ps][e].type;
-          const int epos = last ? pvalid : B.ev[ps][e].pos;
-          if (f_open) {
-            const int take = epos - pos;
-            if (f_store && take > 0) {
-              for (int j = lane; j < take; j += 32) win[f_wpos + j] = c_sub(py[pos + j], dc_open);
-              __threadfence_block();  // samples first, then the counter the decoder (same CTA) polls
-              __syncwarp();
-              if (lane == 0) { *(volatile int*)&B.progress[f_slot] = f_wpos + take; mbar_arrive(&B.bell[f_slot]); }
-            }
-            f_wpos += take;
-            pos = epos;
-          }
-          if (etype == 2) {
-            f_open = false;  // the decoder already has the window: it saw progress reach its length
-            pos = epos;
-          } else if (etype == 1) {
-            const int j = B.ev[ps][e].a;
-            dc_open = make_float2(pe_re[j], pe_im[j]);  // dc_est right after the trigger sample
-            f_store = B.ev[ps][e].c != 0;
-            f_open = true;
-            win = win_base + (B.ev[ps][e].d ? A.rn16_pad : 0);
-            if (f_store) {
-              // the scratch area and the meta slot are reused two hand-offs later
-              while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
-              f_slot = n_signalled & 1;
-              if (lane == 0) {
-                win[0] = c_sub(py[epos], dc_open);
-                const int knd = B.ev[ps][e].d;
-                B.meta_kind[f_slot] = knd; B.meta_ordinal[f_slot] = wsig_ordinal; B.meta_open[f_slot] = B.ev[ps][e].b;
-                B.meta_len[f_slot] = knd ? C.len_epc : C.len_rn16;
-                *(volatile int*)&B.progress[f_slot] = 0;
-                B.aborted[f_slot] = 0;
-              }
-              __threadfence_block();
-              __syncwarp();
-              if (lane == 0) {
-                *(volatile int*)&B.progress[f_slot] = 1;
-                __threadfence_block();
-                mbar_arrive(&B.win_ready[f_slot]);  // hand the window to the decoder NOW (streaming decode)
-              }
-              n_signalled++;
-            }
-            wsig_ordinal++;
-            f_wpos = 1;
-            pos = epos + 1;
-          }
-        }
-        __syncwarp();
-      }
-
+      // ================================================================= E(i-3) is warp C's: ring the bell, carry on with P3
+      const bool need_emit = i >= 3 && i - 3 < ntiles && B.emit[(i - 3) & (kPS - 1)] != 0;
+      if (need_emit && lane == 0) { B.go_tile = i - 3; MBAR_ARRIVE_EXP(&B.go); }
       PP_MARK(3)
       // ================================================================= P3(i-1): thresholds, state machine, DC list
       if (i >= 1 && i - 1 < ntiles) {
         const int t = i - 1, s = t & (kPS - 1);
         int nev = 0, n_e = 0;
+        const bool open_at_start = gate_open;
         const int nvalid = min(kTT, n_out - t * kTT);
         const float* davg = bufA(t);
         const float* ta = ring_a + s * kTT;
@@ -475,7 +648,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
               const int run_start = pos;
               int p_open = -1;
               // (the one-vote result only covers a run that starts the tile with the signal high)
+              PP_SUBB(3)
               if (!have_masks && !(quiet && run_start == 0)) make_masks();
+              PP_SUBB(4)
               if (sig_pos && (lt[0] | lt[1] | lt[2] | lt[3]) == 0u) {
                 // carrier only (the common case): no falling edge can occur, only the open test remains
                 if (num_pulses > kNumPulsesCommand) {
@@ -486,9 +661,16 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
               } else {
                 GateFsm fs = {sig_pos, n_samples, num_pulses};
                 const Mask128 ltm = {{lt[0], lt[1], lt[2], lt[3]}}, gtm = {{gt[0], gt[1], gt[2], gt[3]}};
+#ifdef RFID_B200_FSM_PARALLEL_EDGES
                 p_open = fsm_closed_run(ltm, gtm, run_start, nvalid, C.n_T1, half_pw, fs);
+#elif defined(RFID_B200_FSM_SCALAR_MASKS)
+                p_open = fsm_closed_run_masks(ltm, gtm, run_start, nvalid, C.n_T1, half_pw, fs);
+#else
+                p_open = fsm_closed_run_lanes(ltm, gtm, run_start, nvalid, C.n_T1, half_pw, fs);
+#endif
                 sig_pos = fs.sig_pos; n_samples = fs.n_samples; num_pulses = fs.num_pulses;
               }
+              PP_SUBB(5)
               const bool opened = p_open >= 0;
               pos = opened ? p_open + 1 : nvalid;
               // ---- DC tracker inputs of the closed run [run_start, pos) (gate_impl.cc:141-143; includes the trigger)
@@ -565,31 +747,21 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           const int n16 = (n_e + 15) & ~15;
           if (lane < 16 && n_e + lane < n16) { er[n_e + lane] = -0.0f; ei[n_e + lane] = -0.0f; }
         }
-        if (lane == 0) { B.n_e[s] = n_e; B.n_ev[s] = min(nev, kMaxTileEvents); }
+        if (lane == 0) { B.n_e[s] = n_e; B.n_ev[s] = min(nev, kMaxTileEvents); B.emit[s] = (open_at_start || nev > 0) ? 1 : 0; }
         __syncwarp();
       }
       PP_MARK(4)
-    }
-    if (have) { PP_DUMP(seg) }
-    // ---- end of the segment
-    if (have) {
-      if (f_open && f_store && lane == 0) {
-        // the segment ended inside a window the decoder is already working on: let it run to the end
-        *(volatile int*)&B.aborted[f_slot] = 1;
-        __threadfence_block();
-        *(volatile int*)&B.progress[f_slot] = 1 << 30;
-        mbar_arrive(&B.bell[f_slot]);
+      if (need_emit) {  // warp C has copied tile i-3 out of the ring (it ran alongside P3)
+        mbar_wait(&B.done, go_count & 1u);
+        go_count++;
       }
-      __syncwarp();
-      if (lane == 0) A.counts[seg] = wcount;
+      pair_sync(pair_bar);
     }
-    while (n_signalled - n_freed >= 2) { mbar_wait(&B.win_free[n_freed & 1], (n_freed >> 1) & 1); n_freed++; }
-    if (lane == 0) {
-      B.meta_kind[n_signalled & 1] = -1;
-      __threadfence_block();
-      mbar_arrive(&B.win_ready[n_signalled & 1]);
+    // ---- end of the segment
+    if (have && lane == 0) A.counts[seg] = wcount;
+    if (lane == 0) { B.go_tile = -1; MBAR_ARRIVE_EXP(&B.go); }
     }
-  } else if (warp == G) {
+  } else if (warp == kChainWarpOfs + 2 * G) {
     // ======================================================================================= chain warp
     // lane 8*c + g: running sum c (0 avg_ampl, 1 dc_est.re, 2 dc_est.im) of segment g
     const int comp = lane >> 3, g = lane & 7;
@@ -599,7 +771,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     float acc = 0.f;
     PP_DECL
 #ifdef RFID_B200_PHASE_PROFILE
-    if (blockIdx.x == 0 && A.window_tap) pp_step_log = reinterpret_cast<long long*>(A.window_tap) + (size_t)(A.nseg + gridDim.x) * 8 + 64 * 8;
+    if (blockIdx.x == 0 && A.window_tap) { pp_step_log = reinterpret_cast<long long*>(A.window_tap) + (size_t)(A.nseg + gridDim.x) * 8 + 64 * 8; pp_abs_log = pp_step_log + (448 - 64) * 8; }
 #endif
     for (int i = 0; i < nsteps; i++) {
 #ifdef RFID_B200_PHASE_PROFILE
@@ -626,34 +798,122 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       PP_MARK(2)
     }
     PP_DUMP(A.nseg + blockIdx.x)
+  } else if (warp == (1 - kChainWarpOfs) + 2 * G) {
+    // ======================================================================================= loader warp
+    // lane g streams the raw tiles of segment g through its three stages (TMA bulk copies), as far ahead as warp A frees them
+    const int g = lane;
+    if (g < g_act) {
+      const rfid_b200_segment sg = A.segs[seg0 + g];
+      const int n_out = (int)(sg.length / DECIM);
+      const int ntiles = (n_out + kTT - 1) / kTT;
+      PackSegCtl& B = ctl_all[g];
+      float2* raw = reinterpret_cast<float2*>(smem + A.off_seg + (size_t)g * A.seg_bytes + A.o_raw);
+      // raw tile geometry (as rx_fused_split.cuh)
+        const int odd = (int)(sg.offset & 1ull);
+      const uint32_t fast_bytes = (uint32_t)((DECIM * kTT + 2 * odd) * 8);
+      int fast_tiles = 0;
+      {
+        const long long by_len = ((long long)sg.length - 1 - (long long)DECIM * (kTT - 1)) / ((long long)DECIM * kTT);
+        const long long room = (long long)A.n_raw - (long long)sg.offset + (DECIM - 1) + odd - (DECIM * kTT + 2 * odd);
+        const long long by_buf = room >= 0 ? room / ((long long)DECIM * kTT) : -1;
+        long long f = (by_len < by_buf ? by_len : by_buf) + 1;
+        if (sg.length < (unsigned)(DECIM * kTT)) f = 0;
+        fast_tiles = f < 0 ? 0 : (f > ntiles ? ntiles : (int)f);
+      }
+      const float2* const fast_src = A.iq + sg.offset - (DECIM - 1) - odd;
+      FusedArgs FA;  // issue_tile_load only reads iq / n_raw
+      FA.iq = A.iq; FA.n_raw = A.n_raw;
+      auto load_tile = [&](int k, int rs_) {
+        float2* dst = raw + (size_t)rs_ * A.raw_stage_samples;
+        if (k >= 1 && k < fast_tiles) {
+          mbar_arrive_expect_tx(&B.raw_full[rs_], fast_bytes);
+          tma_load_1d(dst, fast_src + (size_t)k * (DECIM * kTT), fast_bytes, &B.raw_full[rs_]);
+        } else {
+          issue_tile_load<DECIM>(FA, sg, k, dst, &B.raw_full[rs_]);
+        }
+      };
+for (int k = 0; k < ntiles; k++) {
+        const int rs_ = k % kPRawStages;
+        if (k >= kPRawStages) mbar_wait_relaxed(&B.raw_empty[rs_], ((k / kPRawStages) - 1) & 1, 4000);
+        load_tile(k, rs_);
+      }
+    }
   } else {
-    // ======================================================================================= decoder warp
-    const int g = warp - G - 1;
+    // ======================================================================================= warp C: emission + decode
+    // Copies the window samples of a tile (y - dc_est, gate_impl.cc:173,187) from the time ring into this segment's
+    // scratch when warp B asks for it, confirms (the ring slot is recycled one step later), and decodes every window
+    // that closed.  Writer and reader of the scratch are this one warp: no fence, no progress counter, no flow control.
+    const int g = warp - 2 * G - 2;
     if (g < g_act) {
       const int seg = seg0 + g;
+      const int n_out = (int)(A.segs[seg].length / DECIM);
       PackSegCtl& B = ctl_all[g];
       unsigned char* sb = smem + A.off_seg + (size_t)g * A.seg_bytes;
+      const float2* ring_y = reinterpret_cast<const float2*>(sb + A.o_ring_y);
       float2* dstage = reinterpret_cast<float2*>(sb + A.o_dstage);
       float2* const win_base = A.win_scratch + (size_t)seg * A.win_stride;
-      for (int j = 0;; j++) {
-        mbar_wait_relaxed(&B.win_ready[j & 1], (j >> 1) & 1, 20000);  // parked by the hardware until a window arrives
-        const int kind = B.meta_kind[j & 1];
-        if (kind < 0) break;
-        const int ordinal = B.meta_ordinal[j & 1], open_idx = B.meta_open[j & 1], len = B.meta_len[j & 1];
-        const float2* win = win_base + (kind ? A.rn16_pad : 0);
-        WindowDecode wd;
-        decode_window_staged(C, kind, win, len, dstage, A.dstage_samples, wd, (const volatile int*)&B.progress[j & 1], &B.bell[j & 1]);
-        rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
-        const bool aborted = *(volatile int*)&B.aborted[j & 1] != 0;
-        if (lane == 0 && !aborted) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
-#ifndef RFID_B200_PHASE_PROFILE
-        if (A.window_tap) {
-          float2* tap = A.window_tap + ((size_t)seg * A.max_windows + ordinal) * C.len_epc;
-          for (int p = lane; p < len; p += 32) tap[p] = __ldcg(win + p);
+      bool f_open = false, f_store = false;
+      int f_wpos = 0, wsig_ordinal = 0, cur_ordinal = 0, cur_kind = 0, cur_open_idx = 0;
+      float2 dc_open = make_float2(0.f, 0.f);
+      float2* win = win_base;
+      for (uint32_t rq = 0;; rq++) {
+        mbar_wait_relaxed(&B.go, rq & 1u, 20000);  // parked by the hardware until warp B rings
+        const int t = B.go_tile;
+        if (t < 0) break;
+        const int ps = t & (kPS - 1);
+        const float2* py = ring_y + ps * kTT;
+        const float* pe_re = dD + (size_t)((ps * 2 + 0) * G + g) * kPChainBuf;
+        const float* pe_im = dD + (size_t)((ps * 2 + 1) * G + g) * kPChainBuf;
+        const int pvalid = min(kTT, n_out - t * kTT);
+        const int pnev = B.n_ev[ps];
+        int n_closed = 0, c_kind[2] = {0, 0}, c_ord[2] = {0, 0}, c_open[2] = {0, 0};
+        int pos = 0;
+        for (int e = 0; e <= pnev; e++) {
+          const bool last = e == pnev;
+          const int etype = last ? 0 : B.ev[ps][e].type;
+          const int epos = last ? pvalid : B.ev[ps][e].pos;
+          if (f_open) {
+            const int take = epos - pos;
+            if (f_store && take > 0)
+              for (int j = lane; j < take; j += 32) win[f_wpos + j] = c_sub(py[pos + j], dc_open);
+            f_wpos += take;
+            pos = epos;
+          }
+          if (etype == 2) {
+            if (f_open && f_store && n_closed < 2) { c_kind[n_closed] = cur_kind; c_ord[n_closed] = cur_ordinal; c_open[n_closed] = cur_open_idx; n_closed++; }
+            f_open = false;
+            pos = epos;
+          } else if (etype == 1) {
+            const int j = B.ev[ps][e].a;
+            dc_open = make_float2(pe_re[j], pe_im[j]);  // dc_est right after the trigger sample
+            f_store = B.ev[ps][e].c != 0;
+            f_open = true;
+            cur_kind = B.ev[ps][e].d;
+            cur_ordinal = wsig_ordinal++;
+            cur_open_idx = B.ev[ps][e].b;
+            win = win_base + (cur_kind ? A.rn16_pad : 0);
+            if (f_store && lane == 0) win[0] = c_sub(py[epos], dc_open);
+            f_wpos = 1;
+            pos = epos + 1;
+          }
         }
-#endif
         __syncwarp();
-        if (lane == 0) mbar_arrive(&B.win_free[j & 1]);
+        if (lane == 0) MBAR_ARRIVE_EXP(&B.done);  // (release: the ring reads above are complete)
+        for (int k = 0; k < n_closed; k++) {
+          const int kind = c_kind[k], len = kind ? C.len_epc : C.len_rn16;
+          const float2* wv = win_base + (kind ? A.rn16_pad : 0);
+          WindowDecode wd;
+          decode_window_staged(C, kind, wv, len, dstage, A.dstage_samples, wd);
+          rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + c_ord[k];
+          if (lane == 0) store_result(dst, wd, seg, c_ord[k], c_open[k], len, kind);
+#ifndef RFID_B200_PHASE_PROFILE
+          if (A.window_tap) {
+            float2* tap = A.window_tap + ((size_t)seg * A.max_windows + c_ord[k]) * C.len_epc;
+            for (int p2 = lane; p2 < len; p2 += 32) tap[p2] = __ldcg(wv + p2);
+          }
+#endif
+          __syncwarp();
+        }
       }
     }
   }

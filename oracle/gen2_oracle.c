@@ -55,8 +55,16 @@ size_t gen2_oracle_mf(const float* x, size_t n_in, int ntaps, int decim, float* 
 
 size_t gen2_oracle_mf_variant(const float* x, size_t n_in, int ntaps, int decim, float* y, int variant)
 {
-  /* variant 0: canonical; 1: sequential ascending float32; 2: float64 accumulation */
+  /* variant 0: canonical; 1: sequential ascending float32; 2: float64 accumulation; 3: canonical order, every block
+   * sum formed once (what the CPU reference arm times) */
   if (variant == 0) return oracle_mf_boxcar(x, n_in, ntaps, decim, y);
+  if (variant == 3) {
+    float* scratch = (float*)malloc(sizeof(float) * 2 * (n_in / (size_t)decim + (size_t)(ntaps / decim) + 2));
+    if (!scratch) return 0;
+    size_t n = oracle_mf_boxcar_blocked(x, n_in, ntaps, decim, y, scratch);
+    free(scratch);
+    return n;
+  }
   return oracle_mf_boxcar_sequential(x, n_in, ntaps, decim, y, variant == 2);
 }
 
@@ -432,9 +440,22 @@ void gen2_oracle_reduce_stats(const gen2_oracle_cfg* c, const rfid_b200_window_r
   int total_queries = 0;
   for (int s = 0; s < nseg; s++) {
     int n = counts[s] < max_per_seg ? counts[s] : max_per_seg;
-    if (!continuous) { cur_round = 1; cur_slot = 1; n_queries = 1; terminated = 0; }
-    o_session(c, recs + (size_t)s * max_per_seg, n, out, &cur_round, &cur_slot, &n_queries, &terminated);
-    if (!continuous) total_queries += n_queries;
+    if (!continuous) {
+      /* an independent segment is a run of the reference with freshly constructed blocks and reader_state
+       * (SURVEY.md 8e): its stop rule sees only its own tag_reads; the global map is for reporting */
+      static rfid_b200_stats seg; /* (large struct: keep it off the stack; this library is single-threaded test code) */
+      memset(&seg, 0, sizeof(seg));
+      cur_round = 1; cur_slot = 1; n_queries = 1; terminated = 0;
+      o_session(c, recs + (size_t)s * max_per_seg, n, &seg, &cur_round, &cur_slot, &n_queries, &terminated);
+      out->n_epc_correct += seg.n_epc_correct;
+      out->n_windows += seg.n_windows;
+      int nt = seg.n_unique_tags < RFID_B200_MAX_TAGS ? seg.n_unique_tags : RFID_B200_MAX_TAGS;
+      for (int k = 0; k < nt; k++)
+        for (int j = 0; j < seg.tag_reads[k]; j++) o_tag_read(out, seg.tag_id[k]);
+      total_queries += n_queries;
+    } else {
+      o_session(c, recs + (size_t)s * max_per_seg, n, out, &cur_round, &cur_slot, &n_queries, &terminated);
+    }
   }
   out->n_queries_sent = continuous ? n_queries : total_queries;
   out->cur_inventory_round = cur_round;

@@ -71,6 +71,48 @@ static inline size_t oracle_mf_boxcar(const float* x, size_t n_in, int ntaps, in
   return n_out;
 }
 
+
+/* Same values, bit for bit, as oracle_mf_boxcar, computed the way a FIR implementation would: every block sum B(m) is
+ * formed once (the plain form above recomputes each of them ntaps/decim times) and the outputs are sums of q
+ * neighbouring block sums in the canonical ascending order; both loops are simple enough for the compiler to
+ * vectorise ACROSS outputs, which leaves the order of the additions inside each output untouched.  This is what the
+ * CPU reference arm of bench.py times (a fair stand-in for GNU Radio's VOLK-vectorised fir_filter_ccc, whose source is
+ * not in the reference tree); tests/test_oracle.py checks it against oracle_mf_boxcar.
+ * scratch: 2 * (n_in / decim + q + 1) floats (block sums, interleaved). */
+#if defined(__x86_64__) && defined(__GNUC__)
+#define ORACLE_MF_TARGET __attribute__((target("avx2")))   /* additions only: no contraction can occur */
+#else
+#define ORACLE_MF_TARGET
+#endif
+ORACLE_MF_TARGET static inline size_t oracle_mf_boxcar_blocked(const float* x, size_t n_in, int ntaps, int decim, float* y,
+                                                                float* scratch)
+{
+  const long D = decim, q = ntaps / decim, rem = ntaps % decim;
+  const size_t n_out = n_in / (size_t)decim;
+  if (rem != 0 || q < 1 || D < 2) return oracle_mf_boxcar(x, n_in, ntaps, decim, y);  /* partial blocks: plain form */
+  /* B(m), m = -(q-1) .. n_out-1, stored at scratch[2 * (m + q - 1)];  blocks that start before sample 0 */
+  float* Bs = scratch;
+  for (long m = -(q - 1); m <= 0 && m < (long)n_out; m++) {
+    float ar, ai;
+    oracle_mf_partial(x, D * m - D + 1, D * m, &ar, &ai);
+    if (D * m < 0) { ar = 0.0f; ai = 0.0f; }   /* entirely before the capture: the sum of zero terms */
+    Bs[2 * (m + q - 1)] = ar; Bs[2 * (m + q - 1) + 1] = ai;
+  }
+  for (long m = 1; m < (long)n_out; m++) {
+    const float* p = x + 2 * (D * m - D + 1);
+    float ar = p[0], ai = p[1];
+    for (long k = 1; k < D; k++) { ar = ar + p[2 * k]; ai = ai + p[2 * k + 1]; }
+    Bs[2 * (m + q - 1)] = ar; Bs[2 * (m + q - 1) + 1] = ai;
+  }
+  for (long n = 0; n < (long)n_out; n++) {
+    const float* b = Bs + 2 * n;   /* B(n-q+1) */
+    float ar = b[0], ai = b[1];
+    for (long k = 1; k < q; k++) { ar = ar + b[2 * k]; ai = ai + b[2 * k + 1]; }
+    y[2 * n] = ar; y[2 * n + 1] = ai;
+  }
+  return n_out;
+}
+
 /* plain sequential-ascending and float64 variants, used only to show that the decode result
  * does not depend on the summation order */
 static inline size_t oracle_mf_boxcar_sequential(const float* x, size_t n_in, int ntaps, int decim, float* y, int use_double)
