@@ -198,18 +198,18 @@ void make_layout_pack(const RxConfig& c, int G, PackArgs& L)
   L.G = G;
   L.raw_stage_samples = c.decim * kTT + 2;
   int o = 0;
-  L.o_raw = o; o = align_up(o + kPRawStages * L.raw_stage_samples * 8, 16);
-  L.o_ring_y = o; o += kPRing * 8;
-  L.o_ring_a = o; o += kPRing * 4;
+  L.o_raw = o; o = align_up(o + 2 * L.raw_stage_samples * 8, 16);
+  L.o_ring_y = o; o += kRingY * 8;
+  L.o_ring_a = o; o += kRingA * 4;
   L.o_snap = o; o = align_up(o + c.dc_length * 8, 16);
   L.dstage_samples = decode_stage_samples(c.n_tag_bit_f);
   if (L.dstage_samples < c.len_rn16) L.dstage_samples = align_up(c.len_rn16, 8);  // an RN16 window is staged whole
-  L.o_dstage = o; o = align_up(o + L.dstage_samples * 8, 128);
+  L.o_dstage = o; o = align_up(o + L.dstage_samples * 8, 16);
   L.seg_bytes = o;
   int off = 0;
   L.off_dA = off; off += 2 * G * kPChainBuf * 4;
-  L.off_dD = off; off += kPS * 2 * G * kPChainBuf * 4;
-  L.off_seg = align_up(off, 128);
+  L.off_dD = off; off += kPDS * 2 * G * kPChainBuf * 4;
+  L.off_seg = align_up(off, 16);
   L.smem_bytes = L.off_seg + G * L.seg_bytes;
   L.rn16_pad = align_up(c.len_rn16, 16);
   L.win_stride = L.rn16_pad + align_up(c.len_epc, 16);
@@ -475,7 +475,7 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
     P.iq = A.iq; P.n_raw = A.n_raw; P.segs = A.segs; P.nseg = nseg; P.max_windows = A.max_windows;
     P.results = A.results; P.counts = A.counts; P.window_tap = A.window_tap; P.win_scratch = A.win_scratch;
     P.cfg = ctx->cfg;
-    rx_pack_kernel<5, 5><<<(nseg + P.G - 1) / P.G, 32 * (3 * P.G + 2), P.smem_bytes, s>>>(P);
+    rx_pack_kernel<5, 5><<<(nseg + P.G - 1) / P.G, 32 * (4 * P.G + 2), P.smem_bytes, s>>>(P);
   } else {
     fn<<<nseg, fast_path_ok(ctx->cfg) ? kSplitThreads : kFusedThreads, A.smem_bytes, s>>>(A);
   }

@@ -208,6 +208,12 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "memory");
   } while (!ok);
 }
+// wait of a warp that has nothing else to do: test, sleep, test ... (the suspend-time hint of try_wait returns after a few
+// dozen cycles on this part, so a hinted loop spins; an explicit sleep keeps an idle warp out of the issue slots)
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, unsigned sleep_ns)
+{
+  while (!mbar_try_wait(bar, parity)) __nanosleep(sleep_ns);
+}
 // one try_wait with a suspend-time hint: true when the phase of parity `parity` has completed; false after (about) hint_ns
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns)
 {

@@ -52,17 +52,25 @@ __device__ __forceinline__ int crc16_check(const uint32_t bits[4])
 // M == nullptr: |w|^2 is evaluated at every gather of the period search instead of being staged.
 // GLOBAL_W: the window lives in global memory (L2-resident scratch written by another warp of this CTA):
 // read it with ld.global.cg so that no stale L1 line can be observed.
-template <bool GLOBAL_W>
+// SUB_DC: the buffer holds the matched filter's output y and the gate's DC estimate is removed here, at every load
+// (y - dc_est is one exact float subtraction per component, gate_impl.cc:173,187, wherever it is evaluated).
+template <bool GLOBAL_W, bool SUB_DC = false>
 struct WinView {
   const float2* p;
-  __device__ __forceinline__ float2 operator[](int i) const { return GLOBAL_W ? __ldcg(p + i) : p[i]; }
+  float2 dc;
+  __device__ __forceinline__ float2 operator[](int i) const
+  {
+    const float2 v = GLOBAL_W ? __ldcg(p + i) : p[i];
+    return SUB_DC ? c_sub(v, dc) : v;
+  }
 };
 
-template <bool GLOBAL_W>
+template <bool GLOBAL_W, bool SUB_DC = false>
 __device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, const float2* __restrict__ w_ptr,
-                                                   int n_avail, float* __restrict__ M, WindowDecode& out)
+                                                   int n_avail, float* __restrict__ M, WindowDecode& out,
+                                                   float2 dc = make_float2(0.f, 0.f))
 {
-  const WinView<GLOBAL_W> w{w_ptr};
+  const WinView<GLOBAL_W, SUB_DC> w{w_ptr, dc};
   const int lane = threadIdx.x & 31;
   const float n = c.n_tag_bit_f;
 
@@ -237,46 +245,92 @@ __device__ __forceinline__ void progress_wait(ProgressWait* pw, int need)
   asm volatile("fence.acq_rel.cta;" ::: "memory");  // the samples were written (and fenced, CTA scope) before the counter moved
 }
 
+// dc: subtracted from every sample as it is staged (x - (+0.0f) == x for every x, so the default changes nothing).
+// All loads of a fill are issued before the first store (kFillBatch per lane): the fill costs one trip to L2, not one per
+// 32 samples.
+constexpr int kFillBatch = 12;
 __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail,
-                                           ProgressWait* progress = nullptr)
+                                           ProgressWait* progress = nullptr, float2 dc = make_float2(0.f, 0.f))
 {
   const int lane = threadIdx.x & 31;
   __syncwarp();
   progress_wait(progress, min(n_avail, lo + count));
-  for (int p = lane; p < count; p += 32) {
-    const int g = lo + p;
-    stage[p] = (g >= 0 && g < n_avail) ? __ldcg(gw + g) : make_float2(0.f, 0.f);
+  for (int p0 = 0; p0 < count; p0 += 32 * kFillBatch) {
+    float2 v[kFillBatch];
+#pragma unroll
+    for (int k = 0; k < kFillBatch; k++) {
+      const int p = p0 + 32 * k + lane, g = lo + p;
+      v[k] = (p < count && g >= 0 && g < n_avail) ? __ldcg(gw + g) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kFillBatch; k++) {
+      const int p = p0 + 32 * k + lane, g = lo + p;
+      if (p < count) stage[p] = (g >= 0 && g < n_avail) ? c_sub(v[k], dc) : make_float2(0.f, 0.f);
+    }
   }
   __syncwarp();
 }
 
 // same, storing |w|^2 (std::norm: re*re + im*im, separately rounded) instead of the sample
 __device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __restrict__ gw, int lo, int count, int n_avail,
-                                                ProgressWait* progress = nullptr)
+                                                ProgressWait* progress = nullptr, float2 dc = make_float2(0.f, 0.f))
 {
   const int lane = threadIdx.x & 31;
   __syncwarp();
   progress_wait(progress, min(n_avail, lo + count));
-  for (int p = lane; p < count; p += 32) {
-    const int g = lo + p;
-    stage_m[p] = (g >= 0 && g < n_avail) ? c_norm(__ldcg(gw + g)) : 0.0f;
+  for (int p0 = 0; p0 < count; p0 += 32 * kFillBatch) {
+    float2 v[kFillBatch];
+#pragma unroll
+    for (int k = 0; k < kFillBatch; k++) {
+      const int p = p0 + 32 * k + lane, g = lo + p;
+      v[k] = (p < count && g >= 0 && g < n_avail) ? __ldcg(gw + g) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kFillBatch; k++) {
+      const int p = p0 + 32 * k + lane, g = lo + p;
+      if (p < count) stage_m[p] = (g >= 0 && g < n_avail) ? c_norm(c_sub(v[k], dc)) : 0.0f;
+    }
   }
   __syncwarp();
 }
 
-__device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
-                                                     float2* __restrict__ stage, int stage_cap, WindowDecode& out,
-                                                     const volatile int* progress_counter = nullptr, uint64_t* bell = nullptr)
+// ---- the staged decode as a resumable sequence of phases ---------------------------------------------------------------
+// head (tag_sync, h_est, tag_decoder_impl.cc:78-109) -> four 64-step chunks of the symbol-period search (:151-165) ->
+// finish (argmax, 128 bit decisions :171-191, CRC).  Each phase needs the window only up to a known position, so a
+// caller that is still receiving the window (rx_pack.cuh: warp C copies it tile by tile) runs the phases as the samples
+// arrive; decode_window_staged below runs them back to back.  One copy of the arithmetic either way.
+struct WinStream {
+  int phase;     // 0: head pending, 1..4: search chunk (phase - 1) pending, 5: search complete
+  int index;     // first data sample: sync index + 6.5 symbols (:107)
+  int head;      // samples the head staged (an RN16 window is staged whole)
+  float e;       // this lane's running energy of candidate period `lane` (lanes 0..19)
+  float Tt;      // this lane's candidate period
+  float2 h;
+};
+
+__device__ __forceinline__ int win_head_samples(const RxConfig& c, int kind, int n_total, int stage_cap)
 {
-  ProgressWait pw_{progress_counter, bell, 0u};
-  ProgressWait* const progress = progress_counter ? &pw_ : nullptr;
+  return min(stage_cap, kind == RFID_B200_RN16 ? n_total : (int)(c.sync_range + 6.0f * c.n_tag_bit_f) + 2);
+}
+
+// window samples a search chunk reads (exclusive upper bound, clamped to the window)
+__device__ __forceinline__ int win_chunk_need(const RxConfig& c, const WinStream& S, int chunk, int n_total, int stage_cap)
+{
+  const int span = min(2 * stage_cap, (int)(64.0f * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
+  const int lo = (int)f_add(f_mul((float)(64 * chunk), c.t_min), (float)S.index);
+  return min(n_total, lo + span);
+}
+
+// tag_sync + h_est; fills sync_index / score / h of `out` and the stream state
+__device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_total,
+                                                float2* __restrict__ stage, int stage_cap, float2 dc, WinStream& S,
+                                                WindowDecode& out, ProgressWait* progress = nullptr)
+{
   const int lane = threadIdx.x & 31;
   const float n = c.n_tag_bit_f;
   const float half = f_div(n, 2.0f);
-
-  // ---- tag_sync + h_est need w[0 .. sync_range + 5.5 n): one stage fill (an RN16 window fits entirely)
-  const int head = min(stage_cap, kind == RFID_B200_RN16 ? n_avail : (int)(c.sync_range + 6.0f * n) + 2);
-  stage_fill(stage, gw, 0, head, n_avail, progress);
+  const int head = win_head_samples(c, kind, n_total, stage_cap);
+  stage_fill(stage, gw, 0, head, n_total, progress, dc);
   float best = -1.0f;
   int best_i = 0x7fffffff;
   for (int i = lane; i < c.sync_range; i += 32) {
@@ -314,10 +368,57 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
   }
   out.sync_index = max_index;
   out.score = max_corr;
-  const int index = (int)f_add(f_add((float)max_index, f_mul((float)kTagPreambleBits, n)), half);
-  const float2 h = out.h;
   out.bits[0] = out.bits[1] = out.bits[2] = out.bits[3] = 0u;
+  S.index = (int)f_add(f_add((float)max_index, f_mul((float)kTagPreambleBits, n)), half);
+  S.head = head;
+  S.h = out.h;
+  S.e = 0.0f;
+  const int number_steps = 20;
+  S.Tt = f_add(c.t_min, f_div(f_mul((float)(lane < number_steps ? lane : 0), f_sub(c.t_max, c.t_min)), (float)(number_steps - 1)));
+  S.phase = 1;
+}
 
+// 64 steps of the symbol-period search: E_t += M[(int)(i * T_t + index)], i = 64*chunk .. 64*chunk + 63, in order
+__device__ __forceinline__ void win_stream_chunk(const RxConfig& c, const float2* __restrict__ gw, int n_total,
+                                                 float2* __restrict__ stage, int stage_cap, float2 dc, WinStream& S,
+                                                 ProgressWait* progress = nullptr)
+{
+  const int lane = threadIdx.x & 31;
+  const int number_steps = 20;
+  const int chunk = S.phase - 1;
+  const int i0 = 64 * chunk;
+  // Only |w|^2 is needed here (magn_squared_samples, gate_impl.cc:176,186), so the stage holds one float per
+  // sample -- twice the reach of the complex stage: 64 steps per fill.
+  float* stage_m = reinterpret_cast<float*>(stage);
+  const int span = min(2 * stage_cap, (int)(64.0f * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
+  const int lo = (int)f_add(f_mul((float)i0, c.t_min), (float)S.index);  // smallest index any candidate touches
+  stage_fill_norm(stage_m, gw, lo, span, n_total, progress, dc);
+  if (lane < number_steps) {
+    const float findex = (float)S.index, Tt = S.Tt;
+    float fi = (float)i0;                          // (float)i, advanced by exact +1.0f steps
+    float e = S.e;
+#pragma unroll 8
+    for (int i = i0; i < i0 + 64; i++) {
+      const int p = (int)f_add(f_mul(fi, Tt), findex);  // (int)(i * T + index), :161; fi == (float)i exactly
+      e = f_add(e, stage_m[p - lo]);
+      fi = f_add(fi, 1.0f);
+    }
+    S.e = e;
+  }
+  S.phase++;
+}
+
+// RN16: half-bit sampling + tag_detection_RN16 (:114-142, :237-253); EPC: remaining search chunks, argmax, 128 bit
+// decisions, CRC-16.  The whole window must be present.
+__device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
+                                                  float2* __restrict__ stage, int stage_cap, float2 dc, WinStream& S,
+                                                  WindowDecode& out, ProgressWait* progress = nullptr)
+{
+  const int lane = threadIdx.x & 31;
+  const float n = c.n_tag_bit_f;
+  const float half = f_div(n, 2.0f);
+  const int index = S.index;
+  const float2 h = S.h;
   if (kind == RFID_B200_RN16) {
     float jm = (float)index;
     for (int m = 0; m < lane; m++) jm = f_add(jm, half);
@@ -326,7 +427,7 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
     float2 s = make_float2(0.0f, 0.0f);
     if (have) {
       const int k = (int)roundf(jm);
-      s = k < head ? stage[k] : __ldcg(gw + k);
+      s = k < S.head ? stage[k] : c_sub(__ldcg(gw + k), dc);
     }
     out.T = 0.0f;
     out.crc_ok = -1;
@@ -334,10 +435,10 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
       float2 s_next = make_float2(__shfl_down_sync(0xffffffffu, s.x, 1), __shfl_down_sync(0xffffffffu, s.y, 1));
       float res = c_proj(s, s_next, h);
       unsigned pos = __ballot_sync(0xffffffffu, res > 0.0f);
-      unsigned S = 0;
+      unsigned Sg = 0;
 #pragma unroll
-      for (int j = 0; j < 16; j++) S |= ((pos >> (2 * j)) & 1u) << j;
-      unsigned Bv = (S ^ ((S << 1) | 1u)) & 0xFFFFu;
+      for (int j = 0; j < 16; j++) Sg |= ((pos >> (2 * j)) & 1u) << j;
+      unsigned Bv = (Sg ^ ((Sg << 1) | 1u)) & 0xFFFFu;
       unsigned msb = 0;
 #pragma unroll
       for (int j = 0; j < 16; j++) msb |= ((Bv >> j) & 1u) << (31 - j);
@@ -349,28 +450,10 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
     }
     return;
   }
-
-  // ---- symbol-period search (:151-165), 32 steps per stage fill
+  while (S.phase < 5) win_stream_chunk(c, gw, n_avail, stage, stage_cap, dc, S, progress);
   const int number_steps = 20;
   const float min_val = c.t_min, max_val = c.t_max;
-  const float Tt = f_add(min_val, f_div(f_mul((float)(lane < number_steps ? lane : 0), f_sub(max_val, min_val)), (float)(number_steps - 1)));
-  // Only |w|^2 is needed here (magn_squared_samples, gate_impl.cc:176,186), so the stage holds one float per
-  // sample -- twice the reach of the complex stage: 64 steps per fill.
-  float e = 0.0f;
-  float* stage_m = reinterpret_cast<float*>(stage);
-  const int span = min(2 * stage_cap, (int)(64.0f * max_val + 256.0f * (max_val - min_val)) + 8);
-  for (int i0 = 0; i0 < 256; i0 += 64) {
-    const int lo = (int)f_add(f_mul((float)i0, min_val), (float)index);  // smallest index any candidate touches
-    stage_fill_norm(stage_m, gw, lo, span, n_avail, progress);
-    if (lane < number_steps) {
-#pragma unroll 8
-      for (int i = i0; i < i0 + 64; i++) {
-        int p = (int)f_add(f_mul((float)i, Tt), (float)index);  // :161
-        e = f_add(e, stage_m[p - lo]);
-      }
-    }
-  }
-  float energy = lane < number_steps ? e : -1.0f;
+  float energy = lane < number_steps ? S.e : -1.0f;
   int e_idx = lane < number_steps ? lane : 0x7fffffff;
   warp_argmax_first(energy, e_idx);
   const int index_T = e_idx;
@@ -378,28 +461,40 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
   out.T = T;
   // ---- 128 bit decisions (:171-191), 32 pairs per stage fill
   const float twoT = f_mul(2.0f, T);
-  unsigned S[4];
+  unsigned Sg[4];
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const int j0 = r * 32;
     const int lo = (int)f_add(f_mul((float)j0, twoT), (float)index);
-    stage_fill(stage, gw, lo, stage_cap, n_avail, progress);
+    stage_fill(stage, gw, lo, stage_cap, n_avail, progress, dc);
     int j = j0 + lane;
     int a = (int)f_add(f_mul((float)j, twoT), (float)index);
     int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);
     float res = c_proj(stage[a - lo], stage[b - lo], h);
-    S[r] = __ballot_sync(0xffffffffu, res > 0.0f);
+    Sg[r] = __ballot_sync(0xffffffffu, res > 0.0f);
   }
   unsigned carry = 1u;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
-    unsigned prev = (S[r] << 1) | carry;
-    carry = S[r] >> 31;
-    unsigned Bv = S[r] ^ prev;
+    unsigned prev = (Sg[r] << 1) | carry;
+    carry = Sg[r] >> 31;
+    unsigned Bv = Sg[r] ^ prev;
     out.bits[r] = __brev(Bv);
   }
   out.crc_ok = crc16_check(out.bits);
   out.tag_id = (int)((out.bits[3] >> 16) & 0xFFu);
+}
+
+__device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
+                                                     float2* __restrict__ stage, int stage_cap, WindowDecode& out,
+                                                     const volatile int* progress_counter = nullptr, uint64_t* bell = nullptr,
+                                                     float2 dc = make_float2(0.f, 0.f))
+{
+  ProgressWait pw_{progress_counter, bell, 0u};
+  ProgressWait* const progress = progress_counter ? &pw_ : nullptr;
+  WinStream S;
+  win_stream_head(c, kind, gw, n_avail, stage, stage_cap, dc, S, out, progress);
+  win_stream_finish(c, kind, gw, n_avail, stage, stage_cap, dc, S, out, progress);
 }
 
 __device__ __forceinline__ void store_result(rfid_b200_window_result* dst, const WindowDecode& d, int segment, int window,
