@@ -257,7 +257,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "ingest"])
     ap.add_argument("--rounds", type=int, default=None, help="inventory rounds (cfg2/cfg4: per GPU; cfg3: in total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--generator", default="torch", choices=["torch", "native"],
@@ -274,6 +274,8 @@ def main():
 
     if args.config == "cfg5":
         return sweep(args, rank, local_rank, world)
+    if args.config == "ingest":
+        return ingest(args, rank, local_rank)
 
     from gen2_uhf_rfid_reader_b200 import abi, synth
     cfg = dict(CONFIGS[args.config])
@@ -522,6 +524,52 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return 0
+
+
+def ingest(args, rank, local_rank):
+    """SURVEY 8(f)-2 as a measured path: a recorded capture in HOST memory (the on-disk format of misc/data/file_source_test,
+    apps/reader.py:102) -> rfid_b200_ingest_capture_host (sliced upload with the CW-gap segmenter's threshold pass behind
+    every slice, segment table, decode) -> host records.  One GPU."""
+    if rank != 0:
+        return 0
+    import torch
+    from gen2_uhf_rfid_reader_b200 import abi, capi, synth
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    rounds = args.rounds or 1000
+    rx = capi.Gen2Rx(device=local_rank)
+    cap = synth.make_capture(rounds, seed=1234, device=dev)
+    n_raw = cap["iq"].numel()
+    rows = []
+    for kind in ("pinned", "pageable"):
+        h = torch.empty(n_raw, dtype=torch.complex64)
+        if kind == "pinned":
+            h = h.pin_memory()
+        h.copy_(cap["iq"])
+        iq_np = h.numpy()
+        for _ in range(2):
+            segs, recs, counts = rx.ingest_capture_host(iq_np, max_windows=MAX_WINDOWS)
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(max(3, args.steps)):
+            t0 = time.perf_counter()
+            segs, recs, counts = rx.ingest_capture_host(iq_np, max_windows=MAX_WINDOWS)
+            ts.append(time.perf_counter() - t0)
+        t = float(np.median(ts))
+        ok = int(sum((recs[s, k]["crc_ok"] == 1) for s in range(len(segs)) for k in range(min(int(counts[s]), MAX_WINDOWS)) if recs[s, k]["kind"] == 1))
+        rows.append({"host_memory": kind, "seconds_per_call": t, "msamples_per_s": n_raw / t / 1e6, "host_to_device_gbs": 8.0 * n_raw / t / 1e9,
+                     "segments_found": int(len(segs)), "epc_crc_ok": ok, "launches_per_call": rx.last_launch_count()})
+    line = {"metric": METRIC, "value": rows[0]["msamples_per_s"], "unit": "MSamples/s", "n_gpus": 1, "steps": max(3, args.steps), "warmup": 2,
+            "ms_per_step": rows[0]["seconds_per_call"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "ingest: %d-round capture (%.1f MB) in host memory -> segmenter + decode -> host records; wall clock per call, "
+                                   "host<->device copies inside" % (rounds, n_raw * 8 / 1e6), "config": "ingest",
+                       "hbm_bytes_per_sample": "16 algorithmic (the threshold pass and the decode each read the capture once) + 8 written by the upload"},
+            "e2e": {"value": rows[0]["msamples_per_s"], "unit": "MSamples/s", "h2d_bytes_per_step": int(n_raw * 8), "d2h_bytes_per_step": int(rounds * MAX_WINDOWS * 64)},
+            "ingest": rows, "gpu_launches": rows[0]["launches_per_call"] * max(3, args.steps)}
+    print(json.dumps(line))
     return 0
 
 

@@ -27,6 +27,8 @@ struct rfid_b200_ctx {
   RxConfig cfg;
   int device;
   cudaStream_t stream;  // own stream for block mode / host-mode capture calls
+  cudaStream_t copy_stream;  // host-mode capture calls: uploads of the next slice run beside the decode of this one
+  cudaEvent_t ev_slice[4];
   std::string last_error;
   // capture mode
   FusedArgs layout;     // shared-memory carve-up (pointers filled per call)
@@ -53,6 +55,8 @@ struct rfid_b200_ctx {
   void* d_in; size_t d_in_bytes;
   void* d_out; size_t d_out_bytes;
   void* d_m2; size_t d_m2_bytes;
+  void* d_blk; size_t d_blk_bytes;   // block mode: [GateCallOut | out samples | |out|^2] in one block -> ONE D2H per work call
+  void* h_blk; size_t h_blk_bytes;   // its pinned host mirror
   rfid_b200_window_result* d_one;
   // mf block mode
   void* d_mf; size_t d_mf_bytes; long long mf_abs0; long long mf_have; long long mf_next_n;
@@ -311,6 +315,7 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
   ctx->window_tap = nullptr; ctx->last_launches = 0; ctx->timing = false; ctx->kernel_ms = 0.f; ctx->kernel_launches = 0;
   ctx->d_iq = ctx->d_segs = ctx->d_res = ctx->d_cnt = ctx->d_in = ctx->d_out = ctx->d_m2 = ctx->d_mf = nullptr;
   ctx->d_win = nullptr; ctx->d_win_bytes = 0;
+  ctx->d_blk = nullptr; ctx->d_blk_bytes = 0; ctx->h_blk = nullptr; ctx->h_blk_bytes = 0;
   ctx->d_iq_bytes = ctx->d_segs_bytes = ctx->d_res_bytes = ctx->d_cnt_bytes = ctx->d_in_bytes = ctx->d_out_bytes = ctx->d_m2_bytes = ctx->d_mf_bytes = 0;
   ctx->d_gate = nullptr; ctx->d_gate_out = nullptr; ctx->d_one = nullptr;
   ctx->mf_abs0 = 0; ctx->mf_have = 0; ctx->mf_next_n = 0;
@@ -323,6 +328,10 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
   make_layout(cfg, ctx->layout);
   cudaError_t e = cudaSetDevice(p->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  ctx->copy_stream = nullptr;
+  for (int k = 0; k < 4; k++) ctx->ev_slice[k] = nullptr;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&ctx->ev_slice[k], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_gate, sizeof(GateState));
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_gate_out, sizeof(GateCallOut));
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_one, sizeof(rfid_b200_window_result));
@@ -375,7 +384,8 @@ void rfid_b200_destroy(rfid_b200_ctx* ctx)
   drain_timing(ctx);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   ctx->ev_pool.clear();
-  void* ptrs[] = {ctx->d_win, ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
+  if (ctx->h_blk) cudaFreeHost(ctx->h_blk);
+  void* ptrs[] = {ctx->d_blk, ctx->d_win, ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
                   ctx->d_gate, ctx->d_gate_out, ctx->d_one, ctx->d_mask, ctx->d_chunk, ctx->d_bursts, ctx->d_ing,
                   ctx->d_script, ctx->d_sim_res, ctx->d_sim_cnt};
   for (void* p : ptrs)
@@ -384,6 +394,8 @@ void rfid_b200_destroy(rfid_b200_ctx* ctx)
     if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
     if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
   }
+  for (int k = 0; k < 4; k++) if (ctx->ev_slice[k]) cudaEventDestroy(ctx->ev_slice[k]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -431,9 +443,20 @@ int rfid_b200_kernel_time(rfid_b200_ctx* ctx, int reset, float* ms_total, int* l
 
 int rfid_b200_last_launch_count(const rfid_b200_ctx* ctx) { return ctx ? ctx->last_launches : RFID_B200_EINVAL; }
 
+static int decode_capture_impl(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw, const rfid_b200_segment* d_segs, int nseg,
+                               int max_windows_per_segment, rfid_b200_window_result* d_results, int32_t* d_counts,
+                               void* stream, int seg_base);
+
 int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw, const rfid_b200_segment* d_segs, int nseg,
                              int max_windows_per_segment, rfid_b200_window_result* d_results, int32_t* d_counts,
                              void* stream)
+{
+  return decode_capture_impl(ctx, d_iq, n_raw, d_segs, nseg, max_windows_per_segment, d_results, d_counts, stream, 0);
+}
+
+static int decode_capture_impl(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw, const rfid_b200_segment* d_segs, int nseg,
+                               int max_windows_per_segment, rfid_b200_window_result* d_results, int32_t* d_counts,
+                               void* stream, int seg_base)
 {
   if (!ctx || !d_iq || !d_segs || !d_results || !d_counts || nseg < 0 || max_windows_per_segment < 1) return RFID_B200_EINVAL;
   if ((reinterpret_cast<uintptr_t>(d_iq) & 15u) != 0) return RFID_B200_EINVAL;  // TMA bulk source alignment
@@ -455,6 +478,7 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
   A.n_raw = n_raw;
   A.segs = d_segs;
   A.nseg = nseg;
+  A.seg_base = seg_base;
   A.max_windows = max_windows_per_segment;
   A.results = d_results;
   A.counts = d_counts;
@@ -472,7 +496,7 @@ int rfid_b200_decode_capture(rfid_b200_ctx* ctx, const float* d_iq, size_t n_raw
     PackArgs P;
     memset(&P, 0, sizeof(P));
     make_layout_pack(ctx->cfg, pack_segments_per_cta(ctx, nseg), P);
-    P.iq = A.iq; P.n_raw = A.n_raw; P.segs = A.segs; P.nseg = nseg; P.max_windows = A.max_windows;
+    P.iq = A.iq; P.n_raw = A.n_raw; P.segs = A.segs; P.nseg = nseg; P.seg_base = seg_base; P.max_windows = A.max_windows;
     P.results = A.results; P.counts = A.counts; P.window_tap = A.window_tap; P.win_scratch = A.win_scratch;
     P.cfg = ctx->cfg;
     rx_pack_kernel<5, 5><<<(nseg + P.G - 1) / P.G, 32 * (4 * P.G + 2), P.smem_bytes, s>>>(P);
@@ -502,15 +526,48 @@ int rfid_b200_decode_capture_host(rfid_b200_ctx* ctx, const float* h_iq, size_t 
   if ((rc = grow(ctx, &ctx->d_res, &ctx->d_res_bytes, res_bytes))) return rc;
   if ((rc = grow(ctx, &ctx->d_cnt, &ctx->d_cnt_bytes, (size_t)nseg * 4))) return rc;
   cudaStream_t s = ctx->stream;
-  CK(cudaMemcpyAsync(ctx->d_iq, h_iq, n_raw * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->d_segs, h_segs, (size_t)nseg * sizeof(rfid_b200_segment), cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(ctx->d_res, 0, res_bytes, s));
-  rc = rfid_b200_decode_capture(ctx, (const float*)ctx->d_iq, n_raw, (const rfid_b200_segment*)ctx->d_segs, nseg,
-                                max_windows_per_segment, (rfid_b200_window_result*)ctx->d_res, (int32_t*)ctx->d_cnt, s);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h_results, ctx->d_res, res_bytes, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h_counts, ctx->d_cnt, (size_t)nseg * 4, cudaMemcpyDeviceToHost, s));
+  // Pinned source: the call is a pipeline over slices of the segment table -- upload of slice k+1 (copy stream) beside the
+  // decode of slice k and the download of slice k-1's records (compute stream).  The call as a whole is bound by the
+  // host -> device link (8 B per sample); the pipeline takes the decode and the record download off its tail.
+  // Pageable source: one plain copy (the driver stages it synchronously anyway).
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, h_iq) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const int n_slices = (pinned && nseg >= 64) ? 4 : 1;
+  if (n_slices == 1) CK(cudaMemcpyAsync(ctx->d_iq, h_iq, n_raw * 8, cudaMemcpyHostToDevice, s));
+  int launches = 0;
+  for (int k = 0; k < n_slices; k++) {
+    const int b = (int)((long long)nseg * k / n_slices), e = (int)((long long)nseg * (k + 1) / n_slices);
+    if (e <= b) continue;
+    if (n_slices > 1) {
+      unsigned long long lo = ~0ull, hi = 0;
+      for (int i = b; i < e; i++) {
+        const unsigned long long o = h_segs[i].offset, t = o + h_segs[i].length;
+        if (o < lo) lo = o;
+        if (t > hi) hi = t;
+      }
+      if (hi > n_raw) hi = n_raw;
+      if (lo > hi) lo = hi;
+      lo = lo >= 4 ? lo - 4 : 0;  // (the tile loader rounds a segment's first sample down to an even index)
+      if (hi > lo) CK(cudaMemcpyAsync((char*)ctx->d_iq + lo * 8, (const char*)h_iq + lo * 8, (hi - lo) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->ev_slice[k], ctx->copy_stream));
+      CK(cudaStreamWaitEvent(s, ctx->ev_slice[k], 0));
+    }
+    rc = decode_capture_impl(ctx, (const float*)ctx->d_iq, n_raw, (const rfid_b200_segment*)ctx->d_segs + b, e - b,
+                             max_windows_per_segment, (rfid_b200_window_result*)ctx->d_res + (size_t)b * max_windows_per_segment,
+                             (int32_t*)ctx->d_cnt + b, s, b);
+    if (rc) return rc;
+    launches += ctx->last_launches;
+    const size_t rb = (size_t)(e - b) * max_windows_per_segment * sizeof(rfid_b200_window_result);
+    CK(cudaMemcpyAsync((char*)h_results + (size_t)b * max_windows_per_segment * sizeof(rfid_b200_window_result),
+                       (char*)ctx->d_res + (size_t)b * max_windows_per_segment * sizeof(rfid_b200_window_result), rb,
+                       cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_counts + b, (int32_t*)ctx->d_cnt + b, (size_t)(e - b) * 4, cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaStreamSynchronize(s));
+  ctx->last_launches = launches;
   return RFID_B200_OK;
 }
 
@@ -1025,22 +1082,32 @@ int rfid_b200_gate_work(rfid_b200_ctx* ctx, int seek, const float* in, int n_in,
   if (n_in == 0 && seek == 0) return RFID_B200_OK;
   CK(cudaSetDevice(ctx->device));
   int rc;
-  const size_t bytes = (size_t)(n_in > 0 ? n_in : 1) * 8;
-  if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_bytes, bytes))) return rc;
-  if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_bytes, bytes))) return rc;
-  if ((rc = grow(ctx, &ctx->d_m2, &ctx->d_m2_bytes, bytes / 2))) return rc;
+  const size_t ns = (size_t)(n_in > 0 ? n_in : 1);
+  // one device block [GateCallOut (64 B) | out: ns complex | |out|^2: ns floats] and its pinned host mirror: the kernel's
+  // whole result comes back with ONE copy and ONE synchronisation per work call (it was two of each)
+  const size_t off_out = 64, off_m2 = off_out + ns * 8, blk = off_m2 + ns * 4;
+  if ((rc = grow(ctx, &ctx->d_in, &ctx->d_in_bytes, ns * 8))) return rc;
+  if ((rc = grow(ctx, &ctx->d_blk, &ctx->d_blk_bytes, blk))) return rc;
+  if (ctx->h_blk_bytes < blk) {
+    if (ctx->h_blk) cudaFreeHost(ctx->h_blk);
+    ctx->h_blk = nullptr; ctx->h_blk_bytes = 0;
+    const size_t want = blk + blk / 4 + 256;
+    if (cudaHostAlloc(&ctx->h_blk, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return RFID_B200_ENOMEM; }
+    ctx->h_blk_bytes = want;
+  }
   cudaStream_t s = ctx->stream;
+  char* db = (char*)ctx->d_blk;
   if (n_in) CK(cudaMemcpyAsync(ctx->d_in, in, (size_t)n_in * 8, cudaMemcpyHostToDevice, s));
-  gate_block_kernel<<<1, 32, 0, s>>>(ctx->cfg, ctx->d_gate, seek, (const float2*)ctx->d_in, n_in, (float2*)ctx->d_out,
-                                     (float*)ctx->d_m2, ctx->d_gate_out);
+  gate_block_kernel<<<1, 32, 0, s>>>(ctx->cfg, ctx->d_gate, seek, (const float2*)ctx->d_in, n_in, (float2*)(db + off_out),
+                                     (float*)(db + off_m2), (GateCallOut*)db);
   CK(cudaGetLastError());
-  GateCallOut r;
-  CK(cudaMemcpyAsync(&r, ctx->d_gate_out, sizeof(r), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->h_blk, db, blk, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  GateCallOut r;
+  memcpy(&r, ctx->h_blk, sizeof(r));
   if (r.written > 0) {
-    CK(cudaMemcpyAsync(out, ctx->d_out, (size_t)r.written * 8, cudaMemcpyDeviceToHost, s));
-    if (magn2_out) CK(cudaMemcpyAsync(magn2_out, ctx->d_m2, (size_t)r.written * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    memcpy(out, (char*)ctx->h_blk + off_out, (size_t)r.written * 8);
+    if (magn2_out) memcpy(magn2_out, (char*)ctx->h_blk + off_m2, (size_t)r.written * 4);
   }
   *consumed = r.consumed; *written = r.written;
   if (closed) *closed = r.closed;
@@ -1083,10 +1150,8 @@ int rfid_b200_mf_work(rfid_b200_ctx* ctx, const float* in, int n_in, float* out,
   if (n_out > out_capacity) return RFID_B200_ECAPACITY;
   int rc;
   const size_t total = (size_t)(ctx->mf_have + n_in);
-  void* nbuf = nullptr; size_t nbytes = 0;
   // staging buffer = carried history + new chunk
   if ((rc = grow(ctx, &ctx->d_out, &ctx->d_out_bytes, (total + 1) * 8))) return rc;
-  (void)nbuf; (void)nbytes;
   cudaStream_t s = ctx->stream;
   if (ctx->mf_have) CK(cudaMemcpyAsync(ctx->d_out, ctx->d_mf, (size_t)ctx->mf_have * 8, cudaMemcpyDeviceToDevice, s));
   if (n_in) CK(cudaMemcpyAsync((char*)ctx->d_out + (size_t)ctx->mf_have * 8, in, (size_t)n_in * 8, cudaMemcpyHostToDevice, s));

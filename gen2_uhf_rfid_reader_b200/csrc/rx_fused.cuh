@@ -79,6 +79,7 @@ struct FusedArgs {
   unsigned long long n_raw;      // total samples in the capture buffer
   const rfid_b200_segment* segs;
   int nseg;
+  int seg_base;                  // added to the segment index stored in the records (a call that decodes a slice of a table)
   int max_windows;               // record slots per segment
   rfid_b200_window_result* results;
   int32_t* counts;
@@ -569,10 +570,10 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
       const float2* win = win_base + (kind ? A.rn16_pad : 0);
       decode_window_warp<true>(C, kind, win, len, nullptr, wd);
       rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
-      if (lane == 0) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
+      if (lane == 0) store_result(dst, wd, seg + A.seg_base, ordinal, open_idx, len, kind);
 #ifndef RFID_B200_PHASE_PROFILE
       if (A.window_tap) {
-        float2* tap = A.window_tap + ((size_t)seg * A.max_windows + ordinal) * C.len_epc;
+        float2* tap = A.window_tap + ((size_t)(seg + A.seg_base) * A.max_windows + ordinal) * C.len_epc;
         for (int p = lane; p < len; p += 32) tap[p] = __ldcg(win + p);
       }
 #endif

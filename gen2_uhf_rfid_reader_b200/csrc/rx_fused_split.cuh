@@ -861,10 +861,10 @@ __global__ void __launch_bounds__(kSplitThreads, 7) rx_fused_split_kernel(const 
       decode_window_staged(C, kind, win, len, dstage, A.dstage_samples, wd, (const volatile int*)&B.progress[j & 1]);
       rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
       const bool aborted = *(volatile int*)&B.aborted[j & 1] != 0;
-      if (lane == 0 && !aborted) store_result(dst, wd, seg, ordinal, open_idx, len, kind);
+      if (lane == 0 && !aborted) store_result(dst, wd, seg + A.seg_base, ordinal, open_idx, len, kind);
 #ifndef RFID_B200_PHASE_PROFILE
       if (A.window_tap) {
-        float2* tap = A.window_tap + ((size_t)seg * A.max_windows + ordinal) * C.len_epc;
+        float2* tap = A.window_tap + ((size_t)(seg + A.seg_base) * A.max_windows + ordinal) * C.len_epc;
         for (int p = lane; p < len; p += 32) tap[p] = __ldcg(win + p);
       }
 #endif

@@ -45,6 +45,7 @@ struct PackArgs {
   unsigned long long n_raw;
   const rfid_b200_segment* segs;
   int nseg;
+  int seg_base;                              // added to the segment index stored in the records
   int max_windows;
   rfid_b200_window_result* results;
   int32_t* counts;
@@ -847,10 +848,10 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           WindowDecode wd;
           decode_window_staged(C, kind, wv, len, dstage, A.dstage_samples, wd, nullptr, nullptr, dc);
           rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + c_ord[k];
-          if (lane == 0) store_result(dst, wd, seg, c_ord[k], c_open[k], len, kind);
+          if (lane == 0) store_result(dst, wd, seg + A.seg_base, c_ord[k], c_open[k], len, kind);
 #ifndef RFID_B200_PHASE_PROFILE
           if (A.window_tap) {
-            float2* tap = A.window_tap + ((size_t)seg * A.max_windows + c_ord[k]) * C.len_epc;
+            float2* tap = A.window_tap + ((size_t)(seg + A.seg_base) * A.max_windows + c_ord[k]) * C.len_epc;
             for (int p2 = lane; p2 < len; p2 += 32) tap[p2] = c_sub(__ldcg(wv + p2), dc);
           }
 #endif
