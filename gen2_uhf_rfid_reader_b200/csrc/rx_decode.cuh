@@ -295,12 +295,14 @@ __device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __
 }
 
 // ---- the staged decode as a resumable sequence of phases ---------------------------------------------------------------
-// head (tag_sync, h_est, tag_decoder_impl.cc:78-109) -> four 64-step chunks of the symbol-period search (:151-165) ->
+// head (tag_sync, h_est, tag_decoder_impl.cc:78-109) -> kSearchChunks chunks of the symbol-period search (:151-165) ->
 // finish (argmax, 128 bit decisions :171-191, CRC).  Each phase needs the window only up to a known position, so a
 // caller that is still receiving the window (rx_pack.cuh: warp C copies it tile by tile) runs the phases as the samples
 // arrive; decode_window_staged below runs them back to back.  One copy of the arithmetic either way.
+constexpr int kChunkSteps = 64;                       // steps of the symbol-period search per phase (one stage fill each)
+constexpr int kSearchChunks = 256 / kChunkSteps;
 struct WinStream {
-  int phase;     // 0: head pending, 1..4: search chunk (phase - 1) pending, 5: search complete
+  int phase;     // 0: head pending, 1..kSearchChunks: search chunk (phase - 1) pending, kSearchChunks + 1: search complete
   int index;     // first data sample: sync index + 6.5 symbols (:107)
   int head;      // samples the head staged (an RN16 window is staged whole)
   float e;       // this lane's running energy of candidate period `lane` (lanes 0..19)
@@ -316,8 +318,8 @@ __device__ __forceinline__ int win_head_samples(const RxConfig& c, int kind, int
 // window samples a search chunk reads (exclusive upper bound, clamped to the window)
 __device__ __forceinline__ int win_chunk_need(const RxConfig& c, const WinStream& S, int chunk, int n_total, int stage_cap)
 {
-  const int span = min(2 * stage_cap, (int)(64.0f * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
-  const int lo = (int)f_add(f_mul((float)(64 * chunk), c.t_min), (float)S.index);
+  const int span = min(2 * stage_cap, (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
+  const int lo = (int)f_add(f_mul((float)(kChunkSteps * chunk), c.t_min), (float)S.index);
   return min(n_total, lo + span);
 }
 
@@ -378,7 +380,7 @@ __device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, con
   S.phase = 1;
 }
 
-// 64 steps of the symbol-period search: E_t += M[(int)(i * T_t + index)], i = 64*chunk .. 64*chunk + 63, in order
+// kChunkSteps steps of the symbol-period search: E_t += M[(int)(i * T_t + index)], i ascending
 __device__ __forceinline__ void win_stream_chunk(const RxConfig& c, const float2* __restrict__ gw, int n_total,
                                                  float2* __restrict__ stage, int stage_cap, float2 dc, WinStream& S,
                                                  ProgressWait* progress = nullptr)
@@ -386,11 +388,10 @@ __device__ __forceinline__ void win_stream_chunk(const RxConfig& c, const float2
   const int lane = threadIdx.x & 31;
   const int number_steps = 20;
   const int chunk = S.phase - 1;
-  const int i0 = 64 * chunk;
-  // Only |w|^2 is needed here (magn_squared_samples, gate_impl.cc:176,186), so the stage holds one float per
-  // sample -- twice the reach of the complex stage: 64 steps per fill.
+  const int i0 = kChunkSteps * chunk;
+  // Only |w|^2 is needed here (magn_squared_samples, gate_impl.cc:176,186), so the stage holds one float per sample.
   float* stage_m = reinterpret_cast<float*>(stage);
-  const int span = min(2 * stage_cap, (int)(64.0f * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
+  const int span = min(2 * stage_cap, (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
   const int lo = (int)f_add(f_mul((float)i0, c.t_min), (float)S.index);  // smallest index any candidate touches
   stage_fill_norm(stage_m, gw, lo, span, n_total, progress, dc);
   if (lane < number_steps) {
@@ -398,7 +399,7 @@ __device__ __forceinline__ void win_stream_chunk(const RxConfig& c, const float2
     float fi = (float)i0;                          // (float)i, advanced by exact +1.0f steps
     float e = S.e;
 #pragma unroll 8
-    for (int i = i0; i < i0 + 64; i++) {
+    for (int i = i0; i < i0 + kChunkSteps; i++) {
       const int p = (int)f_add(f_mul(fi, Tt), findex);  // (int)(i * T + index), :161; fi == (float)i exactly
       e = f_add(e, stage_m[p - lo]);
       fi = f_add(fi, 1.0f);
@@ -450,7 +451,7 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
     }
     return;
   }
-  while (S.phase < 5) win_stream_chunk(c, gw, n_avail, stage, stage_cap, dc, S, progress);
+  while (S.phase <= kSearchChunks) win_stream_chunk(c, gw, n_avail, stage, stage_cap, dc, S, progress);
   const int number_steps = 20;
   const float min_val = c.t_min, max_val = c.t_max;
   float energy = lane < number_steps ? S.e : -1.0f;

@@ -1,3 +1,8 @@
+/* Interface compatibility header: the class / function / constant names, signatures and values declared here are those of
+ * gr-rfid's installed public header of the same name (nkargas/Gen2-UHF-RFID-Reader, Copyright 2014 Nikos Kargas
+ * <nkargas@isc.tuc.gr>, GNU General Public License version 3 or later), because blocks built against it must be
+ * drop-in replacements.  The implementation behind the interface is this repository's own.  This file is distributed
+ * under the GNU General Public License, version 3 or (at your option) any later version; see LICENSE. */
 /* rfid/tag_decoder.h -- public interface of the tag decoder block (drop-in for
  * gr-rfid/include/rfid/tag_decoder.h:35-49).
  *

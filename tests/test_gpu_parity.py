@@ -565,3 +565,105 @@ def test_sim_closed_loop_other_rates(adc, ntaps):
     orecs, ocounts, _ = orc.decode_segments(cap["iq"].cpu().numpy(), segs, max_per_seg=2)
     assert ocounts.tolist() == counts.tolist()
     _assert_same(recs, orecs, "sim adc %d" % adc)
+
+
+# ------------------------------------------------------------------ round 2: packed kernel, sliced host call, Q=4 at size
+@pytest.mark.parametrize("g", [1, 2, 3, 5, 7])
+def test_pack_kernel_any_segments_per_cta(oracle, g, monkeypatch):
+    """rx_pack_kernel with a forced number of segments per CTA (the library picks it from the batch size): ragged
+    lengths, odd offsets, a last CTA that is not full -- every packing decodes like the oracle"""
+    from gen2_uhf_rfid_reader_b200 import capi
+    monkeypatch.setenv("RFID_B200_PACK_G", str(g))
+    rxg = capi.Gen2Rx()
+    cap = synth.make_capture(23, seed=91)
+    iq = cap["iq"].numpy()
+    segs = cap["segments"].copy()
+    rng = np.random.default_rng(g)
+    segs["length"] = (segs["length"] - rng.integers(0, 9000, size=segs.size)).astype(np.uint32)   # ragged ends (mid-window too)
+    segs["offset"] = segs["offset"] + rng.integers(0, 3, size=segs.size).astype(np.uint64)        # odd first samples
+    recs, counts = rxg.decode_capture_host(iq, segs, max_windows=4)
+    orecs, ocounts, _ = oracle.decode_segments(iq, segs, max_per_seg=4)
+    assert counts.tolist() == ocounts.tolist()
+    _assert_same(recs, orecs, "G=%d" % g)
+
+
+def test_split_kernel_still_selectable(oracle, monkeypatch):
+    """RFID_B200_KERNEL=split keeps the one-CTA-per-segment kernel for the reference configuration (A/B against the packed one)"""
+    from gen2_uhf_rfid_reader_b200 import capi
+    monkeypatch.setenv("RFID_B200_KERNEL", "split")
+    rxs = capi.Gen2Rx()
+    cap = synth.make_capture(40, seed=92)
+    iq = cap["iq"].numpy()
+    recs, counts = rxs.decode_capture_host(iq, cap["segments"], max_windows=4)
+    orecs, ocounts, _ = oracle.decode_segments(iq, cap["segments"], max_per_seg=4)
+    assert counts.tolist() == ocounts.tolist()
+    _assert_same(recs, orecs, "split")
+
+
+def test_host_call_from_pinned_memory_is_sliced_and_identical(rx, oracle):
+    """rfid_b200_decode_capture_host pipelines a pinned source over four slices of the segment table (upload k+1 beside
+    decode k): same records, global segment indices, as the one-shot device call and the oracle"""
+    import torch
+    from gen2_uhf_rfid_reader_b200 import capi
+    cap = synth.make_capture(200, seed=93)
+    h = cap["iq"].pin_memory()
+    iq = h.numpy()
+    segs = cap["segments"]
+    recs, counts = rx.decode_capture_host(iq, segs, max_windows=2)
+    assert rx.last_launch_count() == 4
+    orecs, ocounts, _ = oracle.decode_segments(iq, segs, max_per_seg=2)
+    assert counts.tolist() == ocounts.tolist()
+    _assert_same(recs, orecs, "sliced host call")
+    assert (recs[:, 0]["segment"] == np.arange(200)).all()
+
+
+def test_cfg4_slots_at_scale_bit_exact():
+    """BASELINE.json configs[3] shape at a size the oracle finishes in seconds: 256 rounds x 16 slots = 4096 slot segments,
+    8 tags (empty, single and collided slots), every record against the Q=4 oracle (bench.py --config cfg4 checks a
+    sample of the full 160,000)"""
+    import torch
+    from gen2_uhf_rfid_reader_b200 import capi
+    from oracle.pyoracle import Oracle
+    dev = torch.device("cuda:0")
+    rx4 = capi.Gen2Rx(fixed_q=4)
+    cap = synth.make_capture(4096, seed=94, device=dev, fixed_q=4, n_tags=8)
+    segs = capi.segments_to_device(cap["segments"], dev)
+    res, cnt = rx4.decode_capture(cap["iq"], segs, max_windows=2)
+    torch.cuda.synchronize()
+    recs, counts = capi.results_to_numpy(res, cnt, 2)
+    orecs, ocounts, _ = Oracle(fixed_q=4).decode_segments(cap["iq"].cpu().numpy(), cap["segments"], max_per_seg=2)
+    assert counts.tolist() == ocounts.tolist()
+    _assert_same(recs, orecs, "cfg4 x 4096")
+    nrep = np.asarray(cap["truth"]["n_replies"])
+    assert (nrep == 0).any() and (nrep == 1).any() and (nrep > 1).any()      # all three slot kinds are in the sample
+    single = nrep == 1
+    assert (recs[single, 1]["crc_ok"] == 1).all()                           # a lone tag always gets through
+    st = rx4.reduce_stats(recs, counts, continuous=False)
+    ost = Oracle(fixed_q=4).reduce_stats(orecs, ocounts, False)
+    assert (st.n_epc_correct, st.n_windows, st.n_unique_tags) == (ost.n_epc_correct, ost.n_windows, ost.n_unique_tags)
+
+
+def test_cabsf_shortcut_never_disagrees_on_the_recording(rx, oracle, cfg1_iq):
+    """the packed kernel evaluates |y| with one Newton step on rsqrt and falls back to the exact double sqrt near a
+    rounding boundary (rx_common.cuh: cabsf_quick); tools/micro/cabs_check.cu sweeps 7e9 inputs -- here: every window
+    sample of the reference's recording through the tap, byte for byte against the gate's own output"""
+    import torch
+    from gen2_uhf_rfid_reader_b200 import capi
+    dev = torch.device("cuda:0")
+    n = 300000 - 300000 % 5
+    iq = torch.from_numpy(cfg1_iq[:n].copy()).to(dev)
+    segs = capi.segments_to_device(abi.make_segments([0], [n]), dev)
+    tap = torch.zeros((64, rx.len_epc), dtype=torch.complex64, device=dev)
+    rx.set_window_tap(tap)
+    try:
+        res, cnt = rx.decode_capture(iq, segs, max_windows=64)
+        torch.cuda.synchronize()
+    finally:
+        rx.set_window_tap(None)
+    nwin = int(cnt.cpu()[0])
+    g = oracle.gate(oracle.mf(cfg1_iq[:n]), max_windows=64, want_windows=True)
+    assert nwin == min(g["n"], 64) and nwin >= 30
+    t = tap.cpu().numpy()
+    for k in range(nwin):
+        L = rx.len_epc if k & 1 else rx.len_rn16
+        assert t[k, :L].tobytes() == g["windows"][k, :L].tobytes(), k

@@ -112,6 +112,41 @@ def test_mf_order_does_not_change_decisions(oracle, cfg1_iq):
         assert np.max(np.abs(o["score"] - outs[0]["score"]) / outs[0]["score"]) < 2e-4
 
 
+def test_blocked_matched_filter_is_the_canonical_one(oracle):
+    """The CPU reference arm of bench.py times the canonical boxcar with every block sum formed once (variant 3):
+    it must be the canonical order bit for bit, for any length and tap count"""
+    rng = np.random.default_rng(5)
+    for n in (0, 3, 5, 24, 25, 26, 777, 16960, 16963):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        assert oracle.mf(x, 0).tobytes() == oracle.mf(x, 3).tobytes(), n
+    from oracle.pyoracle import Oracle
+    for adc, ntaps in ((1000000, 12), (1000000, 13), (4000000, 50)):
+        o = Oracle(adc_rate=adc, ntaps=ntaps)
+        x = (rng.standard_normal(5000) + 1j * rng.standard_normal(5000)).astype(np.complex64)
+        assert o.mf(x, 0).tobytes() == o.mf(x, 3).tobytes(), (adc, ntaps)
+
+
+def test_independent_segments_have_their_own_stop_rule():
+    """continuous=0: a segment is a reference run with fresh blocks and reader_state, so the unique-tag stop rule
+    (gate_impl.cc:101-104) sees only the segment's own tags; the global tag map is for reporting only"""
+    from gen2_uhf_rfid_reader_b200 import abi
+    from oracle.pyoracle import Oracle
+    o = Oracle(max_tags=1)
+    recs = np.zeros((3, 4), dtype=abi.RESULT_DTYPE)
+    for s in range(3):
+        for k in range(4):
+            recs[s, k]["kind"] = k & 1
+            recs[s, k]["crc_ok"] = 1 if k & 1 else -1
+            recs[s, k]["tag_id"] = 10 * s + k      # every EPC a different tag: 2 per segment, 6 globally
+    counts = np.full(3, 4, dtype=np.int32)
+    st = o.reduce_stats(recs, counts, False)
+    # per segment: 2 EPC windows, the second one makes 2 unique tags > max_tags = 1 -> stop AFTER it; all 12 windows count
+    assert st.n_windows == 12 and st.n_epc_correct == 6 and st.n_unique_tags == 6
+    st_c = o.reduce_stats(recs, counts, True)
+    # one continuous run: stops after the second unique tag, i.e. after 4 windows
+    assert st_c.n_windows == 4 and st_c.n_epc_correct == 2
+
+
 def test_crc_known_answers(oracle):
     assert oracle.query_bits(0) == "1000000000000000010000"   # file_sink content / SURVEY Appendix B
     assert oracle.query_bits(4) == "1000000000000010011101"
