@@ -249,6 +249,30 @@ __device__ __forceinline__ void progress_wait(ProgressWait* pw, int need)
 // All loads of a fill are issued before the first store (kFillBatch per lane): the fill costs one trip to L2, not one per
 // 32 samples.
 constexpr int kFillBatch = 12;
+__device__ __forceinline__ float2 ld_ca_f2(const float2* p)
+{
+  float2 v;
+  asm volatile("ld.global.ca.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+// touch the cache lines of window samples [lo, lo + count) (clamped to the window): lane l loads one word of line l.
+// Returns a value the caller must keep alive (asm volatile("" :: "f"(x))) until it no longer minds waiting for the loads.
+__device__ __forceinline__ float l1_touch_span(const float2* __restrict__ gw, int lo, int count, int n_avail)
+{
+  const int lane = threadIdx.x & 31;
+  const int first = max(lo, 0), last = min(lo + count, n_avail) - 1;   // samples
+  float d = 0.0f;
+  if (last >= first) {
+    const unsigned long long a0 = reinterpret_cast<unsigned long long>(gw + first) & ~127ull;
+    const unsigned long long a1 = reinterpret_cast<unsigned long long>(gw + last);
+    const unsigned long long a = a0 + 128ull * (unsigned)lane;
+    if (a <= a1) {
+      const unsigned long long aa = a < reinterpret_cast<unsigned long long>(gw) ? reinterpret_cast<unsigned long long>(gw) : a;
+      asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(d) : "l"(aa));
+    }
+  }
+  return d;
+}
 __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail,
                                            ProgressWait* progress = nullptr, float2 dc = make_float2(0.f, 0.f))
 {
@@ -272,6 +296,8 @@ __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restri
 }
 
 // same, storing |w|^2 (std::norm: re*re + im*im, separately rounded) instead of the sample
+// L1: load through the SM's L1 (ld.global.ca) instead of L2 only -- for callers that touched the lines beforehand
+template <bool L1 = false>
 __device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __restrict__ gw, int lo, int count, int n_avail,
                                                 ProgressWait* progress = nullptr, float2 dc = make_float2(0.f, 0.f))
 {
@@ -283,7 +309,7 @@ __device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __
 #pragma unroll
     for (int k = 0; k < kFillBatch; k++) {
       const int p = p0 + 32 * k + lane, g = lo + p;
-      v[k] = (p < count && g >= 0 && g < n_avail) ? __ldcg(gw + g) : make_float2(0.f, 0.f);
+      v[k] = (p < count && g >= 0 && g < n_avail) ? (L1 ? ld_ca_f2(gw + g) : __ldcg(gw + g)) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int k = 0; k < kFillBatch; k++) {
@@ -333,6 +359,9 @@ __device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, con
   const float half = f_div(n, 2.0f);
   const int head = win_head_samples(c, kind, n_total, stage_cap);
   stage_fill(stage, gw, 0, head, n_total, progress, dc);
+  // (whole window present: start the first search chunk's lines towards L1 now; it begins 6.5 symbols after the sync index)
+  float sink = 0.0f;
+  if (!progress && kind != RFID_B200_RN16) sink = l1_touch_span(gw, (int)(6.5f * n), 32 * 16, n_total);
   float best = -1.0f;
   int best_i = 0x7fffffff;
   for (int i = lane; i < c.sync_range; i += 32) {
@@ -378,6 +407,7 @@ __device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, con
   const int number_steps = 20;
   S.Tt = f_add(c.t_min, f_div(f_mul((float)(lane < number_steps ? lane : 0), f_sub(c.t_max, c.t_min)), (float)(number_steps - 1)));
   S.phase = 1;
+  asm volatile("" ::"f"(sink));
 }
 
 // kChunkSteps steps of the symbol-period search: E_t += M[(int)(i * T_t + index)], i ascending
@@ -413,7 +443,7 @@ __device__ __forceinline__ void win_stream_chunk(const RxConfig& c, const float2
 // decisions, CRC-16.  The whole window must be present.
 __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
                                                   float2* __restrict__ stage, int stage_cap, float2 dc, WinStream& S,
-                                                  WindowDecode& out, ProgressWait* progress = nullptr)
+                                                  WindowDecode& out, ProgressWait* progress = nullptr, long long* pp = nullptr)
 {
   const int lane = threadIdx.x & 31;
   const float n = c.n_tag_bit_f;
@@ -449,9 +479,43 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
       out.crc_ok = -2;
       out.tag_id = -1;
     }
+    if (pp && lane == 0) { pp[2] = pp[3] = pp[4] = clock64(); }
     return;
   }
-  while (S.phase <= kSearchChunks) win_stream_chunk(c, gw, n_avail, stage, stage_cap, dc, S, progress);
+  if (!progress) {
+    // ---- remaining chunks of the symbol-period search, whole window present (nobody to wait for): while chunk k's 64
+    // steps run from the stage, chunk k+1's cache lines travel from L2 into this SM's L1 (one touch per lane and line, the
+    // value is never used), so that its fill is a short trip.  The scratch was written by this warp before the decode began
+    // and an SM's own stores keep its L1 coherent; the streaming caller (progress != null) keeps the L2-only loads.
+    // (Tried: all 32 lanes gathering 16 steps x 20 candidates into a table that lane t then adds up in order -- fewer
+    // instructions, but slower than the plain loop below: 19.6 k vs 15.6 k cycles per window.)
+    float* stage_m = reinterpret_cast<float*>(stage);
+    const int span = min(2 * stage_cap, (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
+    while (S.phase <= kSearchChunks) {
+      const int i0 = kChunkSteps * (S.phase - 1);
+      const int lo = (int)f_add(f_mul((float)i0, c.t_min), (float)index);
+      stage_fill_norm<true>(stage_m, gw, lo, span, n_avail, nullptr, dc);
+      float sink = 0.0f;
+      if (S.phase < kSearchChunks) sink = l1_touch_span(gw, (int)f_add(f_mul((float)(i0 + kChunkSteps), c.t_min), (float)index), span, n_avail);
+      if (lane < 20) {
+        const float findex = (float)index, Tt = S.Tt;
+        float fi = (float)i0;
+        float e = S.e;
+#pragma unroll 8
+        for (int i = i0; i < i0 + kChunkSteps; i++) {
+          const int p = (int)f_add(f_mul(fi, Tt), findex);  // (int)(i * T + index), :161; fi == (float)i exactly
+          e = f_add(e, stage_m[p - lo]);
+          fi = f_add(fi, 1.0f);
+        }
+        S.e = e;
+      }
+      asm volatile("" ::"f"(sink));  // the touch may complete any time before here
+      S.phase++;
+    }
+  } else {
+    while (S.phase <= kSearchChunks) win_stream_chunk(c, gw, n_avail, stage, stage_cap, dc, S, progress);
+  }
+  if (pp && lane == 0) pp[2] = clock64();
   const int number_steps = 20;
   const float min_val = c.t_min, max_val = c.t_max;
   float energy = lane < number_steps ? S.e : -1.0f;
@@ -463,17 +527,42 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
   // ---- 128 bit decisions (:171-191), 32 pairs per stage fill
   const float twoT = f_mul(2.0f, T);
   unsigned Sg[4];
+  if (!progress) {
+    // the whole window is present: every lane gathers its eight samples straight from L2, all loads in flight together
+    float2 wa[4], wb[4];
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const int j0 = r * 32;
-    const int lo = (int)f_add(f_mul((float)j0, twoT), (float)index);
-    stage_fill(stage, gw, lo, stage_cap, n_avail, progress, dc);
-    int j = j0 + lane;
-    int a = (int)f_add(f_mul((float)j, twoT), (float)index);
-    int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);
-    float res = c_proj(stage[a - lo], stage[b - lo], h);
-    Sg[r] = __ballot_sync(0xffffffffu, res > 0.0f);
+    for (int r = 0; r < 4; r++) {
+      const int j = r * 32 + lane;
+      const int a = (int)f_add(f_mul((float)j, twoT), (float)index);
+      const int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);
+      const bool ia = a >= 0 && a < n_avail, ib = b >= 0 && b < n_avail;   // (outside the window: 0, as the stage fill does)
+      wa[r] = ia ? __ldcg(gw + a) : dc;
+      wb[r] = ib ? __ldcg(gw + b) : dc;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int j = r * 32 + lane;
+      const int a = (int)f_add(f_mul((float)j, twoT), (float)index);
+      const int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);
+      const float2 sa = (a >= 0 && a < n_avail) ? c_sub(wa[r], dc) : make_float2(0.f, 0.f);
+      const float2 sb = (b >= 0 && b < n_avail) ? c_sub(wb[r], dc) : make_float2(0.f, 0.f);
+      const float res = c_proj(sa, sb, h);
+      Sg[r] = __ballot_sync(0xffffffffu, res > 0.0f);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int j0 = r * 32;
+      const int lo = (int)f_add(f_mul((float)j0, twoT), (float)index);
+      stage_fill(stage, gw, lo, stage_cap, n_avail, progress, dc);
+      int j = j0 + lane;
+      int a = (int)f_add(f_mul((float)j, twoT), (float)index);
+      int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);
+      float res = c_proj(stage[a - lo], stage[b - lo], h);
+      Sg[r] = __ballot_sync(0xffffffffu, res > 0.0f);
+    }
   }
+  if (pp && lane == 0) pp[3] = clock64();
   unsigned carry = 1u;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
@@ -484,18 +573,21 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
   }
   out.crc_ok = crc16_check(out.bits);
   out.tag_id = (int)((out.bits[3] >> 16) & 0xFFu);
+  if (pp && lane == 0) pp[4] = clock64();
 }
 
 __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
                                                      float2* __restrict__ stage, int stage_cap, WindowDecode& out,
                                                      const volatile int* progress_counter = nullptr, uint64_t* bell = nullptr,
-                                                     float2 dc = make_float2(0.f, 0.f))
+                                                     float2 dc = make_float2(0.f, 0.f), long long* pp = nullptr)
 {
   ProgressWait pw_{progress_counter, bell, 0u};
   ProgressWait* const progress = progress_counter ? &pw_ : nullptr;
   WinStream S;
+  if (pp && (threadIdx.x & 31) == 0) pp[0] = clock64();
   win_stream_head(c, kind, gw, n_avail, stage, stage_cap, dc, S, out, progress);
-  win_stream_finish(c, kind, gw, n_avail, stage, stage_cap, dc, S, out, progress);
+  if (pp && (threadIdx.x & 31) == 0) pp[1] = clock64();
+  win_stream_finish(c, kind, gw, n_avail, stage, stage_cap, dc, S, out, progress, pp);
 }
 
 __device__ __forceinline__ void store_result(rfid_b200_window_result* dst, const WindowDecode& d, int segment, int window,

@@ -244,14 +244,8 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
   float* const dA = reinterpret_cast<float*>(smem + A.off_dA);   // [2][G][kPChainBuf]
   float* const dD = reinterpret_cast<float*>(smem + A.off_dD);   // [kPDS][2][G][kPChainBuf]
 
-  // ---- init: zero the time rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56), barriers
-  for (int g = 0; g < G; g++) {
-    unsigned char* sb = smem + A.off_seg + (size_t)g * A.seg_bytes;
-    float2* ry = reinterpret_cast<float2*>(sb + A.o_ring_y);
-    float* ra = reinterpret_cast<float*>(sb + A.o_ring_a);
-    for (int i = threadIdx.x; i < kRingY; i += blockDim.x) ry[i] = make_float2(0.f, 0.f);
-    for (int i = threadIdx.x; i < kRingA; i += blockDim.x) ra[i] = 0.f;
-  }
+  // ---- init: barriers first, so that the loader warp can start the first raw half-tiles on their way while the other
+  // warps zero the time rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56)
   if (threadIdx.x < G) {
     PackSegCtl& c = ctl_all[threadIdx.x];
     for (int s = 0; s < 2; s++) { mbar_init(&c.raw_full[s], 1); mbar_init(&c.raw_empty[s], s == 0 ? 2 : 1); mbar_init(&c.dc_rdy[s], 1); }
@@ -260,14 +254,25 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     for (int s = 0; s < kPDS; s++) { c.n_e[s] = 0; c.n_ev[s] = 0; c.emit[s] = 0; }
     mbar_fence_init();
   }
-  // lockstep length: the longest segment of the CTA
+  __syncthreads();
   int max_tiles = 0;
-  for (int g = 0; g < g_act; g++) {
-    const int n_out_g = (int)(A.segs[seg0 + g].length / DECIM);
-    max_tiles = max(max_tiles, (n_out_g + kT2 - 1) / kT2);
+  if (warp != 3 * G) {
+    for (int g = 0; g < G; g++) {
+      unsigned char* sb = smem + A.off_seg + (size_t)g * A.seg_bytes;
+      float4* ry = reinterpret_cast<float4*>(sb + A.o_ring_y);
+      float4* ra = reinterpret_cast<float4*>(sb + A.o_ring_a);
+      const int tid = threadIdx.x - (warp > 3 * G ? 32 : 0), nth = blockDim.x - 32;
+      for (int i = tid; i < kRingY / 2; i += nth) ry[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < kRingA / 4; i += nth) ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // lockstep length: the longest segment of the CTA
+    for (int g = 0; g < g_act; g++) {
+      const int n_out_g = (int)(A.segs[seg0 + g].length / DECIM);
+      max_tiles = max(max_tiles, (n_out_g + kT2 - 1) / kT2);
+    }
+    asm volatile("bar.sync 15, %0;" ::"r"((int)blockDim.x - 32) : "memory");   // everybody but the loader warp
   }
   const int nsteps = max_tiles + 3;
-  __syncthreads();
 
   if (warp < 3 * G) {
     // ======================================================================================= warps A0 / A1 (P1) and B (P3)
@@ -846,7 +851,11 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           if (kind) n_dc[1]++; else n_dc[0]++;
           const float2 dc = B.dc_val[kind];
           WindowDecode wd;
+#ifdef RFID_B200_PHASE_PROFILE
+          decode_window_staged(C, kind, wv, len, dstage, A.dstage_samples, wd, nullptr, nullptr, dc, pp_log ? pp_log + (kind ? 60 : 61) * 8 : nullptr);
+#else
           decode_window_staged(C, kind, wv, len, dstage, A.dstage_samples, wd, nullptr, nullptr, dc);
+#endif
           rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + c_ord[k];
           if (lane == 0) store_result(dst, wd, seg + A.seg_base, c_ord[k], c_open[k], len, kind);
 #ifndef RFID_B200_PHASE_PROFILE

@@ -35,5 +35,6 @@ for i in range(steps):
     print("%3d | %7d %7d %7d %7d | %7d %7d %7d %7d | %7d %7d %7d | %7d %7d %7d" %
           (i, A[i][0], A[i][1], A[i][2], A[i][3], B[i][0], B[i][1], B[i][2], B[i][3], CH[i][0], CH[i][1], CH[i][2], C[i][0], C[i][1], C[i][2]))
 
-d = C[60]
-print("EPC decode of segment 0 (cycles): head+sync %d, period search %d, bits+crc %d, total %d" % (d[1] - d[0], d[2] - d[1], d[3] - d[2], d[3] - d[0]))
+for name, d in (("EPC", C[60]), ("RN16", C[61])):
+    print("%s decode of segment 0 (cycles): head+sync %d, period search %d, bit samples %d, bits+crc %d, total %d" %
+          (name, d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[4] - d[0]))
