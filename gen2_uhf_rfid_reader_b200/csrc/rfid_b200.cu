@@ -48,7 +48,8 @@ struct rfid_b200_ctx {
   void* d_segs; size_t d_segs_bytes;
   void* d_res; size_t d_res_bytes;
   void* d_cnt; size_t d_cnt_bytes;
-  void* d_win; size_t d_win_bytes;  // per-segment window scratch of the fused kernel
+  void* d_win; size_t d_win_bytes;  // per-segment window scratch of the one-CTA-per-segment kernels
+  void* d_yhist;                     // rx_pack_kernel: y history, [%nsmid][kPMaxSeg][kYW] float2
   // block mode
   GateState* d_gate;
   GateCallOut* d_gate_out;
@@ -193,8 +194,22 @@ void make_layout(const RxConfig& c, FusedArgs& L)
   L.smem_bytes = off;
 }
 
-// rx_pack_kernel serves the reference configuration (block-sum matched filter with 5 blocks of 5, rings inside a tile)
-bool pack_ok(const RxConfig& c) { return c.decim == 5 && c.mf_rem == 0 && c.mf_q == 5 && fast_path_ok(c); }
+// number of SM identifiers (%smid < %nsmid; may exceed the SM count)
+__global__ void query_nsmid_kernel(unsigned* out)
+{
+  unsigned n;
+  asm("mov.u32 %0, %%nsmid;" : "=r"(n));
+  *out = n;
+}
+
+// rx_pack_kernel serves the reference configuration (block-sum matched filter with 5 blocks of 5, rings inside a tile);
+// its y history must hold a whole EPC window plus the tiles warps A / B / C may be apart, and at most kPTrig windows can
+// open within one tile
+bool pack_ok(const RxConfig& c)
+{
+  return c.decim == 5 && c.mf_rem == 0 && c.mf_q == 5 && fast_path_ok(c) && c.len_rn16 >= kT2 / 2 &&
+         c.len_epc + c.dc_length + 8 * kT2 <= kYW;
+}
 
 // shared-memory carve-up of rx_pack_kernel for G segments per CTA
 void make_layout_pack(const RxConfig& c, int G, PackArgs& L)
@@ -205,18 +220,16 @@ void make_layout_pack(const RxConfig& c, int G, PackArgs& L)
   L.o_raw = o; o = align_up(o + 2 * L.raw_stage_samples * 8, 16);
   L.o_ring_y = o; o += kRingY * 8;
   L.o_ring_a = o; o += kRingA * 4;
-  L.o_snap = o; o = align_up(o + c.dc_length * 8, 16);
   L.dstage_samples = decode_stage_samples(c.n_tag_bit_f);
   if (L.dstage_samples < c.len_rn16) L.dstage_samples = align_up(c.len_rn16, 8);  // an RN16 window is staged whole
   L.o_dstage = o; o = align_up(o + L.dstage_samples * 8, 16);
   L.seg_bytes = o;
   int off = 0;
-  L.off_dA = off; off += 2 * G * kPChainBuf * 4;
+  L.off_dA = off; off += kPAS * G * kPChainBuf * 4;
   L.off_dD = off; off += kPDS * 2 * G * kPChainBuf * 4;
   L.off_seg = align_up(off, 16);
   L.smem_bytes = L.off_seg + G * L.seg_bytes;
-  L.rn16_pad = align_up(c.len_rn16, 16);
-  L.win_stride = L.rn16_pad + align_up(c.len_epc, 16);
+  if (L.smem_bytes < kPackMinSmem) L.smem_bytes = kPackMinSmem;   // one CTA per SM: the y history is indexed by the SM
 }
 
 int pack_segments_per_cta(const rfid_b200_ctx* ctx, int nseg);
@@ -315,6 +328,7 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
   ctx->window_tap = nullptr; ctx->last_launches = 0; ctx->timing = false; ctx->kernel_ms = 0.f; ctx->kernel_launches = 0;
   ctx->d_iq = ctx->d_segs = ctx->d_res = ctx->d_cnt = ctx->d_in = ctx->d_out = ctx->d_m2 = ctx->d_mf = nullptr;
   ctx->d_win = nullptr; ctx->d_win_bytes = 0;
+  ctx->d_yhist = nullptr;
   ctx->d_blk = nullptr; ctx->d_blk_bytes = 0; ctx->h_blk = nullptr; ctx->h_blk_bytes = 0;
   ctx->d_iq_bytes = ctx->d_segs_bytes = ctx->d_res_bytes = ctx->d_cnt_bytes = ctx->d_in_bytes = ctx->d_out_bytes = ctx->d_m2_bytes = ctx->d_mf_bytes = 0;
   ctx->d_gate = nullptr; ctx->d_gate_out = nullptr; ctx->d_one = nullptr;
@@ -353,6 +367,19 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
     ctx->pack_disabled = kv && strcmp(kv, "split") == 0;
   }
   if (e == cudaSuccess && pack_ok(cfg)) {
+    // the y history of rx_pack_kernel: one region per SM identifier
+    unsigned nsmid = 0, *d_n = nullptr;
+    e = cudaMalloc(&d_n, sizeof(unsigned));
+    if (e == cudaSuccess) {
+      query_nsmid_kernel<<<1, 1, 0, ctx->stream>>>(d_n);
+      e = cudaMemcpyAsync(&nsmid, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      cudaFree(d_n);
+    }
+    if (e == cudaSuccess && nsmid < (unsigned)prop.multiProcessorCount) nsmid = prop.multiProcessorCount;
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_yhist, (size_t)nsmid * kPMaxSeg * kYW * sizeof(float2));
+  }
+  if (e == cudaSuccess && pack_ok(cfg)) {
     PackArgs pl;
     make_layout_pack(cfg, kPMaxSeg, pl);
     e = cudaFuncSetAttribute((const void*)rx_pack_kernel<5, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
@@ -385,7 +412,7 @@ void rfid_b200_destroy(rfid_b200_ctx* ctx)
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   ctx->ev_pool.clear();
   if (ctx->h_blk) cudaFreeHost(ctx->h_blk);
-  void* ptrs[] = {ctx->d_blk, ctx->d_win, ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
+  void* ptrs[] = {ctx->d_blk, ctx->d_win, ctx->d_yhist, ctx->d_iq, ctx->d_segs, ctx->d_res, ctx->d_cnt, ctx->d_in, ctx->d_out, ctx->d_m2, ctx->d_mf,
                   ctx->d_gate, ctx->d_gate_out, ctx->d_one, ctx->d_mask, ctx->d_chunk, ctx->d_bursts, ctx->d_ing,
                   ctx->d_script, ctx->d_sim_res, ctx->d_sim_cnt};
   for (void* p : ptrs)
@@ -467,7 +494,8 @@ static int decode_capture_impl(rfid_b200_ctx* ctx, const float* d_iq, size_t n_r
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;  // NULL = the (legacy) default stream, as documented
   FusedArgs A = ctx->layout;
-  {
+  const bool use_pack = pack_ok(ctx->cfg) && !ctx->pack_disabled;
+  if (!use_pack) {
     // window scratch: one RN16 + one EPC window per segment (grown on demand; cudaMalloc synchronises, so a
     // caller that wants a fully asynchronous call sizes the context once with its largest batch)
     int rc = grow(ctx, &ctx->d_win, &ctx->d_win_bytes, (size_t)nseg * A.win_stride * sizeof(float2));
@@ -492,12 +520,12 @@ static int decode_capture_impl(rfid_b200_ctx* ctx, const float* d_iq, size_t n_r
     }
     CK(cudaEventRecord(e0, s));
   }
-  if (pack_ok(ctx->cfg) && !ctx->pack_disabled) {
+  if (use_pack) {
     PackArgs P;
     memset(&P, 0, sizeof(P));
     make_layout_pack(ctx->cfg, pack_segments_per_cta(ctx, nseg), P);
     P.iq = A.iq; P.n_raw = A.n_raw; P.segs = A.segs; P.nseg = nseg; P.seg_base = seg_base; P.max_windows = A.max_windows;
-    P.results = A.results; P.counts = A.counts; P.window_tap = A.window_tap; P.win_scratch = A.win_scratch;
+    P.results = A.results; P.counts = A.counts; P.window_tap = A.window_tap; P.y_hist = reinterpret_cast<float2*>(ctx->d_yhist);
     P.cfg = ctx->cfg;
     rx_pack_kernel<5, 5><<<(nseg + P.G - 1) / P.G, 32 * (4 * P.G + 2), P.smem_bytes, s>>>(P);
   } else {

@@ -248,6 +248,13 @@ __device__ __forceinline__ void progress_wait(ProgressWait* pw, int need)
 // dc: subtracted from every sample as it is staged (x - (+0.0f) == x for every x, so the default changes nothing).
 // All loads of a fill are issued before the first store (kFillBatch per lane): the fill costs one trip to L2, not one per
 // 32 samples.
+// Where a window lives in global memory: sample g of the window is base[(ofs + g) & mask].  mask = -1: a plain array; the
+// pack kernel's windows lie in a circular per-segment history of y (mask = its size - 1, ofs = the window's first sample).
+struct WinSrc {
+  const float2* base;
+  int ofs, mask;
+  __device__ __forceinline__ const float2* at(int g) const { return base + ((ofs + g) & mask); }
+};
 constexpr int kFillBatch = 12;
 __device__ __forceinline__ float2 ld_ca_f2(const float2* p)
 {
@@ -257,23 +264,16 @@ __device__ __forceinline__ float2 ld_ca_f2(const float2* p)
 }
 // touch the cache lines of window samples [lo, lo + count) (clamped to the window): lane l loads one word of line l.
 // Returns a value the caller must keep alive (asm volatile("" :: "f"(x))) until it no longer minds waiting for the loads.
-__device__ __forceinline__ float l1_touch_span(const float2* __restrict__ gw, int lo, int count, int n_avail)
+__device__ __forceinline__ float l1_touch_span(const WinSrc gw, int lo, int count, int n_avail)
 {
   const int lane = threadIdx.x & 31;
-  const int first = max(lo, 0), last = min(lo + count, n_avail) - 1;   // samples
+  const int first = max(lo, 0), last = min(lo + count, n_avail) - 1;   // samples; a line holds 16 of them
   float d = 0.0f;
-  if (last >= first) {
-    const unsigned long long a0 = reinterpret_cast<unsigned long long>(gw + first) & ~127ull;
-    const unsigned long long a1 = reinterpret_cast<unsigned long long>(gw + last);
-    const unsigned long long a = a0 + 128ull * (unsigned)lane;
-    if (a <= a1) {
-      const unsigned long long aa = a < reinterpret_cast<unsigned long long>(gw) ? reinterpret_cast<unsigned long long>(gw) : a;
-      asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(d) : "l"(aa));
-    }
-  }
+  const int smp = min(first + 16 * lane, last);
+  if (last >= first && first + 16 * lane < last + 16) asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(d) : "l"(gw.at(smp)));
   return d;
 }
-__device__ __forceinline__ void stage_fill(float2* stage, const float2* __restrict__ gw, int lo, int count, int n_avail,
+__device__ __forceinline__ void stage_fill(float2* stage, const WinSrc gw, int lo, int count, int n_avail,
                                            ProgressWait* progress = nullptr, float2 dc = make_float2(0.f, 0.f))
 {
   const int lane = threadIdx.x & 31;
@@ -284,7 +284,7 @@ __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restri
 #pragma unroll
     for (int k = 0; k < kFillBatch; k++) {
       const int p = p0 + 32 * k + lane, g = lo + p;
-      v[k] = (p < count && g >= 0 && g < n_avail) ? __ldcg(gw + g) : make_float2(0.f, 0.f);
+      v[k] = (p < count && g >= 0 && g < n_avail) ? __ldcg(gw.at(g)) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int k = 0; k < kFillBatch; k++) {
@@ -298,7 +298,7 @@ __device__ __forceinline__ void stage_fill(float2* stage, const float2* __restri
 // same, storing |w|^2 (std::norm: re*re + im*im, separately rounded) instead of the sample
 // L1: load through the SM's L1 (ld.global.ca) instead of L2 only -- for callers that touched the lines beforehand
 template <bool L1 = false>
-__device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __restrict__ gw, int lo, int count, int n_avail,
+__device__ __forceinline__ void stage_fill_norm(float* stage_m, const WinSrc gw, int lo, int count, int n_avail,
                                                 ProgressWait* progress = nullptr, float2 dc = make_float2(0.f, 0.f))
 {
   const int lane = threadIdx.x & 31;
@@ -309,7 +309,7 @@ __device__ __forceinline__ void stage_fill_norm(float* stage_m, const float2* __
 #pragma unroll
     for (int k = 0; k < kFillBatch; k++) {
       const int p = p0 + 32 * k + lane, g = lo + p;
-      v[k] = (p < count && g >= 0 && g < n_avail) ? (L1 ? ld_ca_f2(gw + g) : __ldcg(gw + g)) : make_float2(0.f, 0.f);
+      v[k] = (p < count && g >= 0 && g < n_avail) ? (L1 ? ld_ca_f2(gw.at(g)) : __ldcg(gw.at(g))) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int k = 0; k < kFillBatch; k++) {
@@ -350,7 +350,7 @@ __device__ __forceinline__ int win_chunk_need(const RxConfig& c, const WinStream
 }
 
 // tag_sync + h_est; fills sync_index / score / h of `out` and the stream state
-__device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_total,
+__device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, const WinSrc gw, int n_total,
                                                 float2* __restrict__ stage, int stage_cap, float2 dc, WinStream& S,
                                                 WindowDecode& out, ProgressWait* progress = nullptr)
 {
@@ -411,7 +411,7 @@ __device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, con
 }
 
 // kChunkSteps steps of the symbol-period search: E_t += M[(int)(i * T_t + index)], i ascending
-__device__ __forceinline__ void win_stream_chunk(const RxConfig& c, const float2* __restrict__ gw, int n_total,
+__device__ __forceinline__ void win_stream_chunk(const RxConfig& c, const WinSrc gw, int n_total,
                                                  float2* __restrict__ stage, int stage_cap, float2 dc, WinStream& S,
                                                  ProgressWait* progress = nullptr)
 {
@@ -441,7 +441,7 @@ __device__ __forceinline__ void win_stream_chunk(const RxConfig& c, const float2
 
 // RN16: half-bit sampling + tag_detection_RN16 (:114-142, :237-253); EPC: remaining search chunks, argmax, 128 bit
 // decisions, CRC-16.  The whole window must be present.
-__device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
+__device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, const WinSrc gw, int n_avail,
                                                   float2* __restrict__ stage, int stage_cap, float2 dc, WinStream& S,
                                                   WindowDecode& out, ProgressWait* progress = nullptr, long long* pp = nullptr)
 {
@@ -458,7 +458,7 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
     float2 s = make_float2(0.0f, 0.0f);
     if (have) {
       const int k = (int)roundf(jm);
-      s = k < S.head ? stage[k] : c_sub(__ldcg(gw + k), dc);
+      s = k < S.head ? stage[k] : c_sub(__ldcg(gw.at(k)), dc);
     }
     out.T = 0.0f;
     out.crc_ok = -1;
@@ -536,8 +536,8 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
       const int a = (int)f_add(f_mul((float)j, twoT), (float)index);
       const int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);
       const bool ia = a >= 0 && a < n_avail, ib = b >= 0 && b < n_avail;   // (outside the window: 0, as the stage fill does)
-      wa[r] = ia ? __ldcg(gw + a) : dc;
-      wb[r] = ib ? __ldcg(gw + b) : dc;
+      wa[r] = ia ? __ldcg(gw.at(a)) : dc;
+      wb[r] = ib ? __ldcg(gw.at(b)) : dc;
     }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -576,7 +576,7 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
   if (pp && lane == 0) pp[4] = clock64();
 }
 
-__device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ gw, int n_avail,
+__device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const WinSrc gw, int n_avail,
                                                      float2* __restrict__ stage, int stage_cap, WindowDecode& out,
                                                      const volatile int* progress_counter = nullptr, uint64_t* bell = nullptr,
                                                      float2 dc = make_float2(0.f, 0.f), long long* pp = nullptr)
@@ -588,6 +588,14 @@ __device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind
   win_stream_head(c, kind, gw, n_avail, stage, stage_cap, dc, S, out, progress);
   if (pp && (threadIdx.x & 31) == 0) pp[1] = clock64();
   win_stream_finish(c, kind, gw, n_avail, stage, stage_cap, dc, S, out, progress, pp);
+}
+
+__device__ __forceinline__ void decode_window_staged(const RxConfig& c, int kind, const float2* __restrict__ w, int n_avail,
+                                                     float2* __restrict__ stage, int stage_cap, WindowDecode& out,
+                                                     const volatile int* progress_counter = nullptr, uint64_t* bell = nullptr,
+                                                     float2 dc = make_float2(0.f, 0.f))
+{
+  decode_window_staged(c, kind, WinSrc{w, 0, -1}, n_avail, stage, stage_cap, out, progress_counter, bell, dc);
 }
 
 __device__ __forceinline__ void store_result(rfid_b200_window_result* dst, const WindowDecode& d, int segment, int window,

@@ -1,44 +1,52 @@
 // rx_pack.cuh -- the roofline kernel of the reference configuration (decimation 5, 25 taps, rings inside one tile):
-// same arithmetic as rx_fused_split.cuh, re-scheduled around two measurements (tools/pack_profile.py):
+// same arithmetic as rx_fused_split.cuh, re-scheduled around three measurements (tools/pack_profile.py, ncu):
 //   * the exact replay of the gate's float running sums (avg_ampl, gate_impl.cc:131; dc_est, gate_impl.cc:141) is a
 //     dependent FADD chain -- it costs the same whether 3 or 24 lanes of the warp carry a chain;
 //   * everything else of a segment is one warp's worth of *latency*, not of issue slots: a warp that walks a tile through
 //     matched filter, |y|, ring differences (or thresholds + the edge / pulse state machine) needs 2-3 thousand cycles per
-//     pass almost independently of how many samples the pass covers.
-// So a CTA owns G <= kPMaxSeg capture segments and runs them in lockstep, one 256-sample tile per step, with one warp per
-// role and segment, and ONE chain warp for all of them:
-//   warp A[g]   P1: waits for the two raw half-tiles (TMA bulk copies issued by the loader warp), block-sum matched
-//               filter, exact |y|, amplitude / DC ring differences of 8 outputs per lane (two groups of 4 consecutive
-//               ones, 128 apart: twice the independent work per dependency chain of the 128-sample version).
-//   chain warp  lane 8*c + g replays running sum c (0 avg_ampl, 1 dc_est.re, 2 dc_est.im) of segment g.
+//     pass almost independently of how many samples the pass covers;
+//   * the stages of a segment have very different costs from tile to tile (the state machine costs 1 k cycles on a
+//     carrier-only tile and 5 k on a tile full of reader pulses), so a lockstep hand-off per tile runs at the sum of the
+//     worst stages.
+// So a CTA owns G <= kPMaxSeg capture segments, one warp per role and segment, ONE chain warp for all of them, and the
+// stages are coupled only through small rings with full / free barriers (mbarriers, one phase per slot use):
+//   warp A0/A1[g] P1: waits for the raw half-tile (TMA bulk copies issued by the loader warp), block-sum matched filter,
+//               exact |y|, amplitude / DC ring differences of 4 outputs per lane.  Writes |y| and the amplitude quotients
+//               into 3-slot rings, the DC quotients into a 4-slot ring, and y itself into the segment's circular history in
+//               global memory (L2 resident, kYW samples).  May run up to three tiles ahead of warp B.
+//   chain warp  lane 8*c + g replays running sum c (0 avg_ampl, 1 dc_est.re, 2 dc_est.im) of segment g: avg_ampl of tile j
+//               as soon as every segment's P1(j) is in, dc_est of tile j-2 once every segment's P3(j-2) has fixed its list;
+//               then hands dc_est at every window's trigger sample to warp C.
 //   warp B[g]   P3: thresholds by ballot, the edge / pulse state machine on 256-bit masks spread over 8 lanes, the DC-ring
-//               differences around gate activity; posts dc_est of every opening window when the chain has produced it.
-//   warp C[g]   copies the window samples of a tile from the time ring to the segment's L2-resident scratch one step
-//               after P3 (as y; dc_est is subtracted when the decoder reads them -- the same exact float subtraction,
-//               gate_impl.cc:173,187), then decodes every window that closed (rx_decode.cuh).  It is the only writer and
-//               the only reader of the scratch: no fence, no progress counter.
+//               differences around gate activity (y read back from the history).  Frees the |y| / quotient slot as soon as
+//               its masks are made.  Registers opening / closing windows in a small queue.
+//   warp C[g]   decodes every closed window straight from the history (rx_decode.cuh); dc_est is subtracted as the
+//               decoder reads the samples -- the same exact float subtraction, gate_impl.cc:173,187.
 //   loader      lane g streams segment g's raw samples through its two half-tile stages as warp A frees them.
-// Hand-offs per step: two named barriers (X: tile ready -> chain, Y: sums ready -> B; a parked warp costs no issue slots),
-// one pair barrier A[g] <-> B[g] (ring slot / sum buffers of the next tile are free), mbarriers for loader and warp C.
-//   step i:  A: P1(i) | arrive X(i) | pair(i)        chain: sync X(i) | avg_ampl(i), dc_est(i-2) | arrive Y(i)
-//            B: sync Y(i-1) | dc of windows opened in tile i-3 | P3(i-1) | C done(i-2)? | ring C for tile i-1 | pair(i)
-// Shared memory per segment: 2 raw half-tile stages (10 KB), a 3-tile time ring of y (6 KB) and a 2-tile ring of |y|
-// (2 KB), ring snapshot; per CTA the running-sum buffers (2 + 4x2 per segment, 1072 B each, skewed so the chain warp's
-// 128-bit accesses are bank-conflict free).  HBM traffic is unchanged: every raw sample is read once, 64 B are written per
-// window (plus the window scratch, which lives in L2).
+// The history is indexed by the SM (one CTA per SM: the shared-memory request guarantees it), so its size does not depend
+// on the number of segments of the launch; warp A never overwrites a sample a queued window still needs.
+// Shared memory per segment: 2 raw half-tile stages (10 KB), warp A's own 2-tile time ring of y (4 KB), a 3-tile ring of
+// |y| (3 KB); per CTA the running-sum buffers (3 + 4x2 per segment, 1072 B each, skewed so the chain warp's 128-bit
+// accesses are bank-conflict free).  HBM traffic: every raw sample is read once, 64 B are written per window; the history
+// (8 B per decimated sample, rewritten in place) lives in L2.
 #pragma once
 
 #include "rx_fused_split.cuh"
 
 namespace rfid_b200 {
 
-constexpr int kT2 = 2 * kTT;                 // decimated samples per step (two half-tiles of kTT)
-constexpr int kRingY = 3 * kT2;              // time ring of y: tile i, i-1 (P3, emission), the tail of i-2 (DC lookback)
-constexpr int kRingA = 2 * kT2;              // time ring of |y|: tile i, i-1
-constexpr int kPDS = 4;                      // DC-list slots: P1 (i), P3 fix-ups (i-1), chain (i-2), dc hand-over (i-3)
+constexpr int kT2 = 2 * kTT;                 // decimated samples per tile (two half-tiles of kTT)
+constexpr int kRingY = 2 * kT2;              // warp A's time ring of y: tile t and t-1 (DC lookback of P1)
+constexpr int kPAS = 3;                      // slots of the |y| ring and of the amplitude quotient / avg_ampl lists
+constexpr int kRingA = kPAS * kT2;
+constexpr int kPDS = 4;                      // DC-list slots: P1 up to three tiles ahead, P3 fix-ups, chain
 constexpr int kPMaxSeg = 7;                  // segments per CTA (chain lanes 8*c + g, g < 8)
 constexpr int kPChainBuf = kT2 + 12;         // floats per running-sum buffer: read-ahead pad; 1072 B = 48 mod 128
 constexpr int kPackMaxThreads = 32 * (4 * kPMaxSeg + 2);   // A0, A1, B, C per segment + loader + chain
+constexpr int kYW = 4096;                    // samples of y history per segment (power of two)
+constexpr int kPQ = 8;                       // queue of windows that will be decoded (opened, not yet decoded)
+constexpr int kPTrig = 2;                    // windows that may open within one tile (host: len_rn16 >= kT2 / 2)
+constexpr int kPackMinSmem = 116 * 1024;     // request at least this much: two CTAs never share an SM (and its history)
 
 struct PackArgs {
   const float2* iq;
@@ -50,13 +58,12 @@ struct PackArgs {
   rfid_b200_window_result* results;
   int32_t* counts;
   float2* window_tap;
-  float2* win_scratch;
-  int win_stride, rn16_pad;
+  float2* y_hist;                            // [%nsmid][kPMaxSeg][kYW]
   RxConfig cfg;
   int G;                                     // segments per CTA of this launch
   int raw_stage_samples;
   int seg_bytes;                             // per-segment shared-memory region
-  int o_raw, o_ring_y, o_ring_a, o_snap, o_dstage;  // offsets inside a segment region
+  int o_raw, o_ring_y, o_ring_a, o_dstage;   // offsets inside a segment region
   int dstage_samples;
   int off_dA, off_dD, off_seg;               // offsets from the dynamic shared-memory base
   int smem_bytes;
@@ -65,16 +72,25 @@ struct PackArgs {
 struct PackSegCtl {
   uint64_t raw_full[2];      // loader (TMA transaction count) -> warp A
   uint64_t raw_empty[2];     // warps A (stage 0: A0 and A1's halo read, stage 1: A1) -> loader
-  uint64_t half_rdy;         // warp A0 -> warp A1: y and |y| of the first half-tile are in the ring
-  float2 keep[2][4];         // warp A1 -> warp A0 (next step): the tile's last MFQ-1 block sums, by tile parity
-  uint64_t go, done;         // warp B -> warp C: "emit tile go_tile" / warp C -> warp B: "copied, the ring slot may go"
-  uint64_t dc_rdy[2];        // warp B -> warp C: dc_est of the window in slot (kind) is in dc_val
-  float2 dc_val[2];
-  int go_tile;               // tile to emit; -1: the segment is over
-  int emit[kPDS];            // does tile t (slot t & 3) contain window samples or gate events?  (written by P3)
-  int n_e[kPDS];
-  int n_ev[kPDS];
-  TileEvent ev[kPDS][kMaxTileEvents];
+  uint64_t half_rdy;         // warp A0 -> warp A1: y and |y| of the first half-tile are in the rings
+  uint64_t tail_rdy;         // warp A1 -> warp A0 (next tile): second half-tile in the rings, block-sum halo in `keep`
+  uint64_t freeA[kPAS];      // warp B -> warps A: masks of the tile in this slot are made, the slot may be rewritten
+  float2 keep[2][4];         // the tile's last MFQ-1 block sums, by tile parity
+  // windows that will be decoded, by sequence number k (slot k & (kPQ-1)): written by warp B, dc_val by the chain warp
+  int q_open[kPQ], q_kind[kPQ], q_ord[kPQ];
+  float2 dc_val[kPQ];
+  volatile int n_opened, n_closed, n_dc, n_decoded, seg_done;
+  // warp B's state that only changes at gate events (kept out of its registers)
+  int b_wcount, b_store, b_nq, b_snap_base, b_queued, b_closed;
+  int n_e[kPDS];             // closed samples of the tile in DC-list slot (written by P3)
+  int trig_n[kPDS];          // queued windows that opened in that tile: index of the trigger in the list, sequence number
+  int trig_j[kPDS][kPTrig], trig_k[kPDS][kPTrig];
+};
+struct PackCtaCtl {
+  uint64_t fullA[kPAS];      // 2G warps A -> chain: P1 of the tile is in
+  uint64_t avgdone[kPAS];    // chain -> warps B: avg_ampl of the tile is final
+  uint64_t p3done[kPDS];     // G warps B -> chain: the tile's DC list is final
+  uint64_t dcdone[kPDS];     // chain -> warps A: the DC-list slot may be rewritten
 };
 
 #ifdef RFID_B200_PHASE_PROFILE
@@ -86,22 +102,8 @@ struct PackSegCtl {
 #define PP_AT(i)
 #endif
 
-enum : int { PBAR_X = 1, PBAR_Y = 3, PBAR_PAIR = 5 };  // + segment slot: warps A and B of one segment
-__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }  // A0, A1, B
-// (bar.arrive / bar.sync order the executing thread's prior shared-memory accesses for the threads that complete the
-// barrier -- the PTX producer/consumer pattern; no separate fence)
-template <int BASE>
-__device__ __forceinline__ void pbar_sync(int parity, int count)
-{
-  if (parity == 0) asm volatile("bar.sync %0, %1;" ::"n"((int)BASE), "r"(count) : "memory");
-  else asm volatile("bar.sync %0, %1;" ::"n"((int)(BASE + 1)), "r"(count) : "memory");
-}
-template <int BASE>
-__device__ __forceinline__ void pbar_arrive(int parity, int count)
-{
-  if (parity == 0) asm volatile("bar.arrive %0, %1;" ::"n"((int)BASE), "r"(count) : "memory");
-  else asm volatile("bar.arrive %0, %1;" ::"n"((int)(BASE + 1)), "r"(count) : "memory");
-}
+// hand-off waits on the critical path: the hardware parks the warp for a few dozen cycles per try
+__device__ __forceinline__ void pwait(uint64_t* bar, uint32_t parity) { mbar_wait_relaxed(bar, parity, 2000); }
 
 // ---- the edge / pulse state machine of one closed run on 256-bit masks, the eight mask words spread over lanes 0..7 ----
 // Same decisions as fsm_closed_run (rx_fused_split.cuh) and therefore as the reference's sample loop
@@ -113,14 +115,14 @@ __device__ __forceinline__ void pbar_arrive(int parity, int count)
 //   opening    the carried state reaches T1 before the first edge, or a rise r with num_pulses > 5 is followed by
 //              n_T1 + 1 edge-free samples inside the tile (gate opens at r + 1 + n_T1; a fall there wins)
 // Positions and counts are combined with redux.sync / vote (one instruction each).
-struct Mask256 { unsigned w[8]; };
 struct GateFsm2 {
   bool sig_pos;
   int n_samples, num_pulses;
 };
 __device__ __forceinline__ unsigned m_below(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)); }
 
-__device__ __forceinline__ int fsm_closed_run_lanes(const Mask256& lt, const Mask256& gt, int from, int nvalid, int n_T1,
+// ltw / gtw: word (lane & 7) of the below- / above-threshold masks, held by the lane itself
+__device__ __forceinline__ int fsm_closed_run_lanes(unsigned ltw, unsigned gtw, int from, int nvalid, int n_T1,
                                                     int half_pw, GateFsm2& st)
 {
   const unsigned FULL = 0xffffffffu;
@@ -128,9 +130,6 @@ __device__ __forceinline__ int fsm_closed_run_lanes(const Mask256& lt, const Mas
   const int w = lane & 7;
   const bool own = lane < 8;
   const int base = 32 * w;
-  unsigned ltw = lt.w[0], gtw = gt.w[0];
-#pragma unroll
-  for (int k = 1; k < 8; k++) { ltw = w == k ? lt.w[k] : ltw; gtw = w == k ? gt.w[k] : gtw; }
   const unsigned live = ~m_below(from - base);
   const unsigned F = ltw & live, R = gtw & live;
   const unsigned Pk = ~(F | R);
@@ -221,6 +220,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
 {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ PackSegCtl ctl_all[kPMaxSeg];
+  __shared__ PackCtaCtl cta;
 #ifdef RFID_B200_PHASE_PROFILE
   __shared__ long long pp_cta_t0;
   if (threadIdx.x == 0) pp_cta_t0 = clock64();
@@ -238,22 +238,30 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
   const int seg0 = blockIdx.x * G;
   const int g_act = min(G, A.nseg - seg0);   // segments this CTA really has
   const RxConfig& C = A.cfg;
-  const int bar_x_count = 32 * (2 * G + 1);   // X: both P1 warps of every segment arrive, the chain warp waits
-  const int bar_count = 32 * (G + 1);         // Y: the chain warp arrives, every B warp waits
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  float2* const y_cta = A.y_hist + (size_t)smid * kPMaxSeg * kYW;
 
-  float* const dA = reinterpret_cast<float*>(smem + A.off_dA);   // [2][G][kPChainBuf]
+  float* const dA = reinterpret_cast<float*>(smem + A.off_dA);   // [kPAS][G][kPChainBuf]
   float* const dD = reinterpret_cast<float*>(smem + A.off_dD);   // [kPDS][2][G][kPChainBuf]
 
   // ---- init: barriers first, so that the loader warp can start the first raw half-tiles on their way while the other
   // warps zero the time rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56)
   if (threadIdx.x < G) {
     PackSegCtl& c = ctl_all[threadIdx.x];
-    for (int s = 0; s < 2; s++) { mbar_init(&c.raw_full[s], 1); mbar_init(&c.raw_empty[s], s == 0 ? 2 : 1); mbar_init(&c.dc_rdy[s], 1); }
-    mbar_init(&c.go, 1); mbar_init(&c.done, 1); mbar_init(&c.half_rdy, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&c.raw_full[s], 1); mbar_init(&c.raw_empty[s], s == 0 ? 2 : 1); }
+    mbar_init(&c.half_rdy, 1); mbar_init(&c.tail_rdy, 1);
+    for (int s = 0; s < kPAS; s++) mbar_init(&c.freeA[s], 1);
     for (int m = 0; m < 4; m++) { c.keep[0][m] = make_float2(0.f, 0.f); c.keep[1][m] = make_float2(0.f, 0.f); }
-    for (int s = 0; s < kPDS; s++) { c.n_e[s] = 0; c.n_ev[s] = 0; c.emit[s] = 0; }
-    mbar_fence_init();
+    for (int s = 0; s < kPDS; s++) { c.n_e[s] = 0; c.trig_n[s] = 0; }
+    c.n_opened = 0; c.n_closed = 0; c.n_dc = 0; c.n_decoded = 0; c.seg_done = 0;
+    c.b_wcount = 0; c.b_store = 0; c.b_nq = 1; c.b_snap_base = 0; c.b_queued = 0; c.b_closed = 0;
   }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kPAS; s++) { mbar_init(&cta.fullA[s], 2 * G); mbar_init(&cta.avgdone[s], 1); }
+    for (int s = 0; s < kPDS; s++) { mbar_init(&cta.p3done[s], G); mbar_init(&cta.dcdone[s], 1); }
+  }
+  if (threadIdx.x < G || threadIdx.x == 32) mbar_fence_init();
   __syncthreads();
   int max_tiles = 0;
   if (warp != 3 * G) {
@@ -265,14 +273,13 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       for (int i = tid; i < kRingY / 2; i += nth) ry[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int i = tid; i < kRingA / 4; i += nth) ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // lockstep length: the longest segment of the CTA
+    // the CTA's barriers count every warp A / B for every tile of the longest segment
     for (int g = 0; g < g_act; g++) {
       const int n_out_g = (int)(A.segs[seg0 + g].length / DECIM);
       max_tiles = max(max_tiles, (n_out_g + kT2 - 1) / kT2);
     }
     asm volatile("bar.sync 15, %0;" ::"r"((int)blockDim.x - 32) : "memory");   // everybody but the loader warp
   }
-  const int nsteps = max_tiles + 3;
 
   if (warp < 3 * G) {
     // ======================================================================================= warps A0 / A1 (P1) and B (P3)
@@ -291,11 +298,10 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     float2* raw = reinterpret_cast<float2*>(sb + A.o_raw);
     float2* ring_y = reinterpret_cast<float2*>(sb + A.o_ring_y);
     float* ring_a = reinterpret_cast<float*>(sb + A.o_ring_a);
-    float2* snap = reinterpret_cast<float2*>(sb + A.o_snap);
-    auto bufA = [&](int tile) { return dA + (size_t)((tile & 1) * G + g) * kPChainBuf; };
+    float2* const y_seg = y_cta + (size_t)g * kYW;
+    auto bufA = [&](int tile) { return dA + (size_t)((tile % kPAS) * G + g) * kPChainBuf; };
     auto bufD = [&](int tile, int comp) { return dD + (size_t)(((tile & (kPDS - 1)) * 2 + comp) * G + g) * kPChainBuf; };
     const float dclen_f = (float)C.dc_length;
-    const int pair_bar = PBAR_PAIR + g;
     PP_DECL
 
     if (is_a) {
@@ -306,12 +312,31 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
 #ifdef RFID_B200_PHASE_PROFILE
       if (seg == 0 && A.window_tap) pp_log = reinterpret_cast<long long*>(A.window_tap) + (h2 ? 256 * 8 : 0);
 #endif
-      for (int i = 0; i < nsteps; i++) {
+      for (int i = 0; i < max_tiles; i++) {
 #ifdef RFID_B200_PHASE_PROFILE
         pp_step = i;
 #endif
         PP_AT(0)
         const int k = 2 * i + h2;                      // half-tile index = tile index of the 128-sample kernels
+        if (have && i < ntiles) {
+          // the slots this tile is written into are free: warp B made the masks of tile i-3, the chain warp is through
+          // with the DC list of tile i-4, and no queued window still needs the history samples about to be replaced
+          if (i >= kPAS) pwait(&B.freeA[i % kPAS], (uint32_t)((i / kPAS - 1) & 1));
+          if (i >= kPDS) pwait(&cta.dcdone[i & (kPDS - 1)], (uint32_t)(((i >> 2) - 1) & 1));
+          if ((i + 1) * kT2 > kYW) {
+            const int lowest = (i + 1) * kT2 - kYW;     // oldest history sample that survives this tile
+            while (true) {
+              const int nd = B.n_decoded, no = B.n_opened;
+              const int need = nd < no ? B.q_open[nd & (kPQ - 1)] : 0x7fffffff;
+              if (B.n_decoded == nd && need >= lowest) break;
+              __nanosleep(200);
+            }
+          }
+        } else if (i >= kPAS) {
+          // nothing to compute (segment over, or no segment): keep step with the CTA so that this warp's arrival can never
+          // fall into an earlier phase of the barrier
+          pwait(&cta.avgdone[i % kPAS], (uint32_t)((i / kPAS - 1) & 1));
+        }
         if (k * kTT < n_out) {
           const int nvalid = min(kTT, n_out - k * kTT);  // outputs of this half-tile
           const int t0 = Q * lane;
@@ -350,9 +375,11 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           // ---- the MFQ-1 block sums before this half-tile (lane 0's halo)
           float2 halo[MFQ - 1];
           if (h2 == 0) {
-            // ... are the last ones of the previous tile: warp A1 left them in the keep slot one step ago
+            // ... are the last ones of the previous tile: warp A1 left them in the keep slot (and the tile's second half in
+            // the time rings, which the lookbacks below reach into)
+            if (i >= 1) pwait(&B.tail_rdy, (uint32_t)((i - 1) & 1));
 #pragma unroll
-            for (int m = 0; m < MFQ - 1; m++) halo[m] = B.keep[(i + 1) & 1][m];   // written while tile i-1 was processed
+            for (int m = 0; m < MFQ - 1; m++) halo[m] = B.keep[(i + 1) & 1][m];
           } else {
             // ... are the last ones of the first half-tile: lanes 0..MFQ-2 recompute them from the tail of stage 0
             mbar_wait(&B.raw_full[0], (uint32_t)(i & 1));
@@ -374,7 +401,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
             const float2 mine = w[Q + m];
             const float ux = __shfl_up_sync(0xffffffffu, mine.x, 1), uy = __shfl_up_sync(0xffffffffu, mine.y, 1);
             w[m] = lane ? make_float2(ux, uy) : halo[m];
-            if (h2 == 1) {  // hand the tile's last block sums to warp A0 (read after the pair barrier)
+            if (h2 == 1) {  // hand the tile's last block sums to warp A0 (read after tail_rdy)
               const float ex = __shfl_sync(0xffffffffu, mine.x, 31), ey = __shfl_sync(0xffffffffu, mine.y, 31);
               if (lane == 0) B.keep[i & 1][m] = make_float2(ex, ey);
             }
@@ -399,20 +426,20 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
 #pragma unroll
             for (int q = 0; q < Q; q++) a[q] = cabsf_ref(y[q].x, y[q].y);
           }
-          const int by = (i % 3) * kT2 + h2 * kTT, ba = (i & 1) * kT2 + h2 * kTT;   // this half-tile's position in the time rings
+          const int by = (i & 1) * kT2 + h2 * kTT, ba = (i % kPAS) * kT2 + h2 * kTT;   // this half-tile's place in the rings
           {
+            const float4 y01 = make_float4(y[0].x, y[0].y, y[1].x, y[1].y), y23 = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
             float4* py = reinterpret_cast<float4*>(ring_y + by + t0);
-            py[0] = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
-            py[1] = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
+            py[0] = y01;
+            py[1] = y23;
             *reinterpret_cast<float4*>(ring_a + ba + t0) = make_float4(a[0], a[1], a[2], a[3]);
+            float4* hy = reinterpret_cast<float4*>(y_seg + ((i * kT2 + h2 * kTT + t0) & (kYW - 1)));   // the history
+            hy[0] = y01;
+            hy[1] = y23;
           }
           PP_AT(2)
           __syncwarp();  // this half-tile's |y| and y visible to the lookbacks below
-          if (h2 == 0) {
-            if (lane == 0 && (k + 1) * kTT < n_out) mbar_arrive(&B.half_rdy);   // A1's lookbacks reach into this half
-          } else {
-            mbar_wait(&B.half_rdy, (uint32_t)(i & 1));
-          }
+          if (h2 == 1) pwait(&B.half_rdy, (uint32_t)(i & 1));   // the lookbacks reach into the first half
           // ---- ring differences (gate_impl.cc:131,141)
           float xd[Q], xr[Q], xi[Q];
           int ia = ba + t0 - C.win_length, iy = by + t0 - C.dc_length;
@@ -452,8 +479,11 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
             mn = fminf(fminf(mn, fabsf(xd[q])), fminf(fabsf(xr[q]), fabsf(xi[q])));
           }
           const bool all_ok = C.win_div_fast && C.dc_div_fast && mn >= kDivFastMin && mx <= kDivFastMax;
+          const bool warp_ok = __all_sync(0xffffffffu, all_ok);
+          // (every lane's lookback values have arrived: warp A1 may go on to this tile's second half)
+          if (h2 == 0 && lane == 0 && (k + 1) * kTT < n_out) mbar_arrive(&B.half_rdy);
           float qd[Q], qr[Q], qi[Q];
-          if (__all_sync(0xffffffffu, all_ok)) {
+          if (warp_ok) {
 #pragma unroll
             for (int q = 0; q < Q; q++) {
               qd[q] = f_div_fast(xd[q], winlen_f, C.win_recip);
@@ -479,10 +509,12 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           *reinterpret_cast<float4*>(bufD(i, 0) + h2 * kTT + t0) = make_float4(qr[0], qr[1], qr[2], qr[3]);
           *reinterpret_cast<float4*>(bufD(i, 1) + h2 * kTT + t0) = make_float4(qi[0], qi[1], qi[2], qi[3]);
           __syncwarp();
+          // second half-tile (and the halo) handed to warp A0's next tile
+          if (h2 == 1 && lane == 0 && (k + 1) * kTT < n_out) mbar_arrive(&B.tail_rdy);
         }
         PP_AT(3)
-        pbar_arrive<PBAR_X>(i & 1, bar_x_count);   // this half of tile i is ready for the chain warp
-        pair_sync(pair_bar);                        // warp B is done with step i: ring slot and sum buffers of tile i+1 are free
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cta.fullA[i % kPAS]);   // this half of tile i is ready for the chain warp
       }
     } else {
       // ------------------------------------------------------------------------------------- warp B: P3
@@ -491,60 +523,47 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       int n_samples = 0, num_pulses = 0;
       bool gate_open = false;
       int to_ungate = C.len_rn16;
-      int wcount = 0, open_idx = 0;
-      bool cur_store = false;
-      int nq = 1;
       bool terminated = false;
       int closed_since = C.dc_length;
-      const int half_pw = C.n_PW / 2;
-      uint32_t go_count = 0;      // emission requests answered by warp C so far (phase parity of the done barrier)
-      bool done_pending = false;
+      // (window count, queries, queue counters, ...: PackSegCtl::b_*, touched at gate events only.  b_snap_base = history
+      // index of the DC ring's oldest entry when the last window opened)
+      // y from the history; before the segment's first sample the rings hold +0 (gate_impl.cc:55-56)
+      auto y_at = [&](int idx) { return idx >= 0 ? __ldcg(y_seg + (idx & (kYW - 1))) : make_float2(0.f, 0.f); };
 #ifdef RFID_B200_PHASE_PROFILE
       if (seg == 0 && A.window_tap) pp_log = reinterpret_cast<long long*>(A.window_tap) + 64 * 8;
 #endif
-      for (int i = 0; i < nsteps; i++) {
+      for (int t = 0; t < max_tiles; t++) {
 #ifdef RFID_B200_PHASE_PROFILE
-        pp_step = i;
+        pp_step = t;
 #endif
         PP_AT(0)
-        if (i >= 1) pbar_sync<PBAR_Y>((i - 1) & 1, bar_count);  // avg_ampl of tile i-1 and dc_est of tile i-3 are final
+        pwait(&cta.avgdone[t % kPAS], (uint32_t)((t / kPAS) & 1));  // avg_ampl of tile t is final
         PP_AT(1)
-        // ---- dc_est right after the trigger sample of every window that opened in tile i-3: hand it to warp C
-        if (i >= 3 && i - 3 < ntiles) {
-          const int t = i - 3, ps = t & (kPDS - 1);
-          const int pnev = B.n_ev[ps];
-          for (int e = 0; e < pnev; e++) {
-            if (B.ev[ps][e].type == 1 && B.ev[ps][e].c != 0 && lane == 0) {  // (windows beyond max_windows are not decoded)
-              const int j = B.ev[ps][e].a, slot = B.ev[ps][e].d;
-              B.dc_val[slot] = make_float2(bufD(t, 0)[j], bufD(t, 1)[j]);
-              mbar_arrive(&B.dc_rdy[slot]);
-            }
-          }
-          __syncwarp();
-        }
-        // ================================================================= P3(i-1): thresholds, state machine, DC list
-        if (i >= 1 && i - 1 < ntiles) {
-          const int t = i - 1, s = t & (kPDS - 1);
-          int nev = 0, n_e = 0;
-          const bool open_at_start = gate_open;
+        // ================================================================= P3(t): thresholds, state machine, DC list
+        if (have && t < ntiles) {
+          // room in the window queue for every window this tile can open (the oldest queued window has closed and its
+          // dc_est is out or on its way: warp C does not depend on this warp to get through it)
+          while (B.b_queued - B.n_decoded > kPQ - 1 - kPTrig) __nanosleep(200);
+          const int s = t & (kPDS - 1);
+          int n_e = 0, ntrig = 0;
           const int nvalid = min(kT2, n_out - t * kT2);
-          const int by = (t % 3) * kT2, ba = (t & 1) * kT2;
+          const int tb = t * kT2;                     // history index of the tile's first sample
           const float* davg = bufA(t);
-          const float* ta = ring_a + ba;
-          const float2* ty = ring_y + by;
+          const float* ta = ring_a + (t % kPAS) * kT2;
           float* er = bufD(t, 0);
           float* ei = bufD(t, 1);
-          bool list_rebuilt = false;
+          bool freed = false;
+          auto release_a = [&]() {   // this tile's |y| and avg_ampl have been read for the last time
+            if (!freed) { __syncwarp(); if (lane == 0) mbar_arrive(&B.freeA[t % kPAS]); freed = true; }
+          };
           if (!terminated && gate_open && to_ungate - n_samples > nvalid) {
             // the whole tile lies inside an open window (gate_impl.cc:182-195): nothing to detect, no DC update
-            n_samples += nvalid;
-            list_rebuilt = true;
+            release_a();
+            n_samples += nvalid;   // (n_e = 0: the chain warp skips the tile)
           } else if (!terminated) {
             // thresholds (gate_impl.cc:136,148,154).  First a one-vote test in the lanes' natural 4-sample groups: while the
             // signal is high and no sample of the tile falls below its threshold, no edge can occur (carrier only).
-            Mask256 lt, gt;
-#pragma unroll
-            for (int r = 0; r < 8; r++) { lt.w[r] = 0u; gt.w[r] = 0u; }
+            unsigned ltw = 0u, gtw = 0u;   // word (lane & 7) of the below- / above-threshold masks
             bool quiet = false;
             if (sig_pos && !gate_open && nvalid == kT2) {
               bool below = false;
@@ -564,18 +583,16 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                 const int p = r * 32 + lane;
                 const float thr = f_mul(davg[p], kThreshFraction);
                 const float av = ta[p];
-                lt.w[r] = __ballot_sync(0xffffffffu, av < thr);
-                gt.w[r] = __ballot_sync(0xffffffffu, av > thr);
+                const unsigned bl = __ballot_sync(0xffffffffu, av < thr), bg = __ballot_sync(0xffffffffu, av > thr);
+                if ((lane & 7) == r) { ltw = bl; gtw = bg; }
               }
               if (nvalid < kT2) {
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                  const unsigned vm = m_below(nvalid - r * 32);
-                  lt.w[r] &= vm;
-                  gt.w[r] &= vm;
-                }
+                const unsigned vm = m_below(nvalid - (lane & 7) * 32);
+                ltw &= vm;
+                gtw &= vm;
               }
               have_masks = true;
+              release_a();
             };
             int pos = 0;
             while (pos < nvalid) {
@@ -586,10 +603,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                 PP_AT(4)
                 if (!have_masks && !(quiet && run_start == 0)) make_masks();
                 PP_AT(5)
-                unsigned any_lt = 0u;
-#pragma unroll
-                for (int r = 0; r < 8; r++) any_lt |= lt.w[r];
-                if (sig_pos && any_lt == 0u) {
+                if (sig_pos && !__any_sync(0xffffffffu, ltw != 0u)) {
                   // carrier only (the common case): no falling edge can occur, only the open test remains
                   if (num_pulses > kNumPulsesCommand) {
                     const int cand = run_start + max(0, C.n_T1 - n_samples);
@@ -598,114 +612,115 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                   if (p_open < 0) n_samples += nvalid - run_start;
                 } else {
                   GateFsm2 fs = {sig_pos, n_samples, num_pulses};
-                  p_open = fsm_closed_run_lanes(lt, gt, run_start, nvalid, C.n_T1, half_pw, fs);
+                  p_open = fsm_closed_run_lanes(ltw, gtw, run_start, nvalid, C.n_T1, C.n_PW / 2, fs);
                   sig_pos = fs.sig_pos; n_samples = fs.n_samples; num_pulses = fs.num_pulses;
                 }
                 PP_AT(6)
                 const bool opened = p_open >= 0;
                 pos = opened ? p_open + 1 : nvalid;
-                // ---- DC tracker inputs of the closed run [run_start, pos) (gate_impl.cc:141-143; includes the trigger)
+                // ---- DC tracker inputs of the closed run [run_start, pos) (gate_impl.cc:141-143; includes the trigger).
+                // The list keeps the tile's natural positions: P1's time-contiguous differences are exact except for the
+                // first dc_length samples after a window, whose ring entries date from before the window -- those are
+                // recomputed here (y from the history); samples inside windows get -0.0f below (x + -0.0f == x).
                 const int len = pos - run_start;
-                if (run_start == 0 && pos == nvalid && !opened && closed_since >= C.dc_length) {
-                  // no gate activity and the ring lookback is time-contiguous: P1's differences are exact
-                } else {
-                  list_rebuilt = true;
+                if (closed_since < C.dc_length) {
+                  const int nfix = min(len, C.dc_length - closed_since);
+                  const int snap0 = B.b_snap_base;
 #pragma unroll 1
-                  for (int j0 = 0; j0 < len; j0 += 32) {
-                    const int j = j0 + lane;
-                    const bool valid = j < len;
-                    const int p = run_start + (valid ? j : 0), m = closed_since + j;
-                    const float2 yv = ty[p];
-                    float2 old;
-                    if (m < C.dc_length) {
-                      old = snap[valid ? m : 0];  // ring contents from before the window
-                    } else {
-                      int iy = by + p - C.dc_length;
-                      if (iy < 0) iy += kRingY;
-                      old = ring_y[iy];
+                  for (int j0 = 0; j0 < nfix; j0 += 64) {
+                    float2 yv[2], ov[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                      const int j = j0 + 32 * u + lane;
+                      const bool valid = j < nfix;
+                      yv[u] = y_at(tb + run_start + (valid ? j : 0));
+                      ov[u] = y_at(snap0 + closed_since + (valid ? j : 0));
                     }
-                    const float xr = valid ? f_sub(yv.x, old.x) : 1.0f, xi = valid ? f_sub(yv.y, old.y) : 1.0f;
-                    float qr, qi;
-                    if (__all_sync(0xffffffffu, C.dc_div_fast && f_div_fast_ok(xr) && f_div_fast_ok(xi))) {
-                      qr = f_div_fast(xr, dclen_f, C.dc_recip);
-                      qi = f_div_fast(xi, dclen_f, C.dc_recip);
-                    } else {
-                      qr = f_div_const(xr, dclen_f, C.dc_recip, C.dc_div_fast);
-                      qi = f_div_const(xi, dclen_f, C.dc_recip, C.dc_div_fast);
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                      const int j = j0 + 32 * u + lane;
+                      const bool valid = j < nfix;
+                      const float xr = valid ? f_sub(yv[u].x, ov[u].x) : 1.0f, xi = valid ? f_sub(yv[u].y, ov[u].y) : 1.0f;
+                      float qr, qi;
+                      if (__all_sync(0xffffffffu, C.dc_div_fast && f_div_fast_ok(xr) && f_div_fast_ok(xi))) {
+                        qr = f_div_fast(xr, dclen_f, C.dc_recip);
+                        qi = f_div_fast(xi, dclen_f, C.dc_recip);
+                      } else {
+                        qr = f_div_const(xr, dclen_f, C.dc_recip, C.dc_div_fast);
+                        qi = f_div_const(xi, dclen_f, C.dc_recip, C.dc_div_fast);
+                      }
+                      if (valid) { er[run_start + j] = qr; ei[run_start + j] = qi; }
                     }
-                    if (valid) { er[n_e + j] = qr; ei[n_e + j] = qi; }
                   }
                 }
                 PP_AT(7)
                 closed_since = min(closed_since + len, 1 << 24);
-                n_e += len;
+                n_e = pos;
                 if (opened) {
-                  // READER COMMAND DETECTED (gate_impl.cc:164-180): keep the dc ring as it stands now
-#pragma unroll 1
-                  for (int j = lane; j < C.dc_length; j += 32) {
-                    int iy = by + (pos - 1) - C.dc_length + 1 + j;
-                    if (iy < 0) iy += kRingY;
-                    snap[j] = ring_y[iy];
-                  }
+                  // READER COMMAND DETECTED (gate_impl.cc:164-180): the DC ring stands as it is now
                   gate_open = true;
-                  open_idx = t * kT2 + pos - 1;
-                  cur_store = wcount < A.max_windows;
-                  if (lane == 0 && nev < kMaxTileEvents) {
-                    TileEvent& ev = B.ev[s][nev];
-                    ev.type = 1; ev.pos = pos - 1; ev.a = n_e - 1; ev.b = open_idx; ev.c = cur_store ? 1 : 0; ev.d = wcount & 1;
+                  const int open_idx = tb + pos - 1, wcount = B.b_wcount, n_queued = B.b_queued;
+                  const bool cur_store = wcount < A.max_windows && ntrig < kPTrig;  // (windows beyond max_windows are not decoded)
+                  __syncwarp();
+                  if (lane == 0) {
+                    B.b_snap_base = open_idx - C.dc_length + 1;
+                    B.b_store = cur_store ? 1 : 0;
+                    if (cur_store) {
+                      // queue the window for warp C; dc_est right after the trigger sample follows from the chain warp
+                      const int qs = n_queued & (kPQ - 1);
+                      B.q_open[qs] = open_idx; B.q_kind[qs] = wcount & 1; B.q_ord[qs] = wcount;
+                      B.trig_j[s][ntrig] = pos - 1; B.trig_k[s][ntrig] = n_queued;
+                      B.b_queued = n_queued + 1;
+                      __threadfence_block();
+                      B.n_opened = n_queued + 1;
+                    }
                   }
-                  nev++;
+                  __syncwarp();
+                  if (cur_store) ntrig++;
                 }
               } else {
-                // ---- open: samples pass through (gate_impl.cc:182-195); warp C copies them out one step later
-                list_rebuilt = true;
+                // ---- open: samples pass through (gate_impl.cc:182-195); warp C reads them from the history.  They do not
+                // enter the DC tracker: their list entries carry the running sums unchanged
                 const int take = min(to_ungate - n_samples, nvalid - pos);
+                for (int j = lane; j < take; j += 32) { er[pos + j] = -0.0f; ei[pos + j] = -0.0f; }
                 n_samples += take; pos += take;
+                n_e = pos;
                 if (n_samples >= to_ungate) {
                   gate_open = false;
+                  const int wcount = B.b_wcount, nq = B.b_nq, ncl = B.b_closed;
+                  const bool stored = B.b_store != 0;
                   const int kind = wcount & 1;  // windows alternate RN16, EPC
-                  if (lane == 0 && nev < kMaxTileEvents) {
-                    TileEvent& ev = B.ev[s][nev];
-                    ev.type = 2; ev.pos = pos; ev.a = kind; ev.b = wcount; ev.c = to_ungate; ev.d = open_idx;
+                  __syncwarp();
+                  if (lane == 0) {
+                    B.b_wcount = wcount + 1;
+                    if (kind) B.b_nq = nq + 1;
+                    if (stored) { B.b_closed = ncl + 1; __threadfence_block(); B.n_closed = ncl + 1; }
                   }
-                  nev++;
-                  wcount++;
+                  __syncwarp();
                   closed_since = 0;
                   // ACK after RN16 -> GATE_SEEK_EPC, Query/QueryRep after EPC -> GATE_SEEK_RN16 (gate_impl.cc:112-123)
                   to_ungate = kind ? C.len_rn16 : C.len_epc;
                   n_samples = 0;
-                  if (kind) {
-                    nq++;
-                    if (nq > C.max_queries) { terminated = true; break; }  // gate_impl.cc:101-109
-                  }
+                  if (kind && nq + 1 > C.max_queries) { terminated = true; break; }  // gate_impl.cc:101-109
                 }
               }
             }
-          } else {
-            list_rebuilt = true;
           }
-          if (list_rebuilt || terminated) {
-            // the closed-sample list is shorter than the tile: pad its last group of 16 with -0.0f (see P1)
+          release_a();
+          if (terminated) {
+            // the list ends where the reader stopped: pad its last group of 16 with -0.0f (see P1)
             const int n16 = (n_e + 15) & ~15;
             if (lane < 16 && n_e + lane < n16) { er[n_e + lane] = -0.0f; ei[n_e + lane] = -0.0f; }
           }
-          if (lane == 0) { B.n_e[s] = n_e; B.n_ev[s] = min(nev, kMaxTileEvents); B.emit[s] = (open_at_start || nev > 0) ? 1 : 0; }
-          __syncwarp();
+          if (lane == 0) { B.n_e[s] = n_e; B.trig_n[s] = ntrig; }
         }
         PP_AT(2)
-        // ---- emission by warp C: tile i-2's copy (requested last step) must be out of the ring before tile i+1 is written
-        if (done_pending) { mbar_wait(&B.done, go_count & 1u); go_count++; done_pending = false; }
-        if (i >= 1 && i - 1 < ntiles && B.emit[(i - 1) & (kPDS - 1)] != 0) {
-          if (lane == 0) { B.go_tile = i - 1; mbar_arrive(&B.go); }
-          done_pending = true;
-        }
-        PP_AT(3)
-        pair_sync(pair_bar);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cta.p3done[t & (kPDS - 1)]);   // the tile's DC list is final
       }
       // ---- end of the segment
-      if (done_pending) { mbar_wait(&B.done, go_count & 1u); go_count++; }
-      if (have && lane == 0) A.counts[seg] = wcount;
-      if (lane == 0) { B.go_tile = -1; mbar_arrive(&B.go); }
+      if (have && lane == 0) A.counts[seg] = B.b_wcount;
+      if (lane == 0) { __threadfence_block(); B.seg_done = 1; }
     }
   } else if (warp == 3 * G + 1) {
     // ======================================================================================= chain warp
@@ -719,29 +734,51 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
 #ifdef RFID_B200_PHASE_PROFILE
     if (blockIdx.x == 0 && A.window_tap) pp_log = reinterpret_cast<long long*>(A.window_tap) + 128 * 8;
 #endif
-    for (int i = 0; i < nsteps; i++) {
+    for (int i = 0; i < max_tiles + 2; i++) {
 #ifdef RFID_B200_PHASE_PROFILE
       pp_step = i;
 #endif
       PP_AT(0)
-      pbar_sync<PBAR_X>(i & 1, bar_x_count);
+      const int t = i - 2;
+      if (i < max_tiles) pwait(&cta.fullA[i % kPAS], (uint32_t)((i / kPAS) & 1));          // P1(i) of every segment
+      if (t >= 0) pwait(&cta.p3done[t & (kPDS - 1)], (uint32_t)((t >> 2) & 1));             // P3(i-2) of every segment
       PP_AT(1)
       {
         // branch-free selection of this lane's buffer and length, then ONE convergent loop for all 24 chains
-        const int t = i - 2;
-        const int n_avg = min(kT2, max(0, n_out - i * kT2));
-        const int n_dc = (active && comp > 0 && i >= 2) ? ctl_all[g].n_e[t & (kPDS - 1)] : 0;
+        const int n_avg = i < max_tiles ? min(kT2, max(0, n_out - i * kT2)) : 0;
+        const int n_dc = (active && comp > 0 && t >= 0) ? ctl_all[g].n_e[t & (kPDS - 1)] : 0;
         const int n = active ? (comp == 0 ? n_avg : n_dc) : 0;
-        const int ofsA = ((i & 1) * G + g) * kPChainBuf;
+        const int ofsA = ((i % kPAS) * G + g) * kPChainBuf;
         const int ofsD = (((t & (kPDS - 1)) * 2 + (comp - 1)) * G + g) * kPChainBuf;
         float* buf = comp == 0 ? dA + ofsA : dD + (active && comp > 0 ? ofsD : 0);
         const int n16 = (n + 15) & ~15;
         __syncwarp();
         chain_inplace(buf, n16, acc);
+        __syncwarp();
+        if (i < max_tiles && lane == 0) mbar_arrive(&cta.avgdone[i % kPAS]);
+        // ---- dc_est right after the trigger sample of every queued window that opened in tile t: hand it to warp C
+        if (t >= 0) {
+          if (active && comp > 0) {
+            PackSegCtl& S = ctl_all[g];
+            const int s = t & (kPDS - 1);
+            const int tn = S.trig_n[s];
+            for (int e = 0; e < tn; e++) {
+              const float v = buf[S.trig_j[s][e]];
+              float* dst = reinterpret_cast<float*>(&S.dc_val[S.trig_k[s][e] & (kPQ - 1)]);
+              dst[comp - 1] = v;
+            }
+          }
+          __syncwarp();
+          if (active && comp == 1) {
+            PackSegCtl& S = ctl_all[g];
+            const int tn = S.trig_n[t & (kPDS - 1)];
+            if (tn > 0) { __threadfence_block(); S.n_dc = S.n_dc + tn; }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cta.dcdone[t & (kPDS - 1)]);
+        }
       }
-      __syncwarp();
       PP_AT(2)
-      if (i + 1 < nsteps) pbar_arrive<PBAR_Y>(i & 1, bar_count);
     }
   } else if (warp == 3 * G) {
     // ======================================================================================= loader warp
@@ -781,91 +818,55 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       }
     }
   } else {
-    // ======================================================================================= warp C: emission + decode
+    // ======================================================================================= warp C: decode
     const int g = warp - 3 * G - 2;
     if (g < g_act) {
       const int seg = seg0 + g;
-      const int n_out = (int)(A.segs[seg].length / DECIM);
       PackSegCtl& B = ctl_all[g];
       unsigned char* sb = smem + A.off_seg + (size_t)g * A.seg_bytes;
-      const float2* ring_y = reinterpret_cast<const float2*>(sb + A.o_ring_y);
       float2* dstage = reinterpret_cast<float2*>(sb + A.o_dstage);
-      float2* const win_base = A.win_scratch + (size_t)seg * A.win_stride;
-      bool f_open = false, f_store = false;
-      int f_wpos = 0, wsig_ordinal = 0, cur_ordinal = 0, cur_kind = 0, cur_open_idx = 0;
-      uint32_t n_dc[2] = {0u, 0u};   // dc_est values taken per slot (phase parity of dc_rdy)
-      float2* win = win_base;
+      const float2* const y_seg = y_cta + (size_t)g * kYW;
       PP_DECL
 #ifdef RFID_B200_PHASE_PROFILE
       if (seg == 0 && A.window_tap) pp_log = reinterpret_cast<long long*>(A.window_tap) + 192 * 8;
 #endif
-      for (uint32_t rq = 0;; rq++) {
-        mbar_wait_idle(&B.go, rq & 1u, 400);  // nothing to do until warp B rings (its deadline is a whole step away)
-        const int t = B.go_tile;
-        if (t < 0) break;
+      for (int k = 0;;) {
+        const int done = B.seg_done;   // (read before the counter: once set, the counter is final)
+        const int nc = B.n_closed;
+        if (nc <= k) {
+          if (done) break;
+          __nanosleep(400);            // nothing to do until warp B closes a window
+          continue;
+        }
 #ifdef RFID_B200_PHASE_PROFILE
-        pp_step = t;
+        pp_step = k;
 #endif
         PP_AT(0)
-        const int ps = t & (kPDS - 1);
-        const float2* py = ring_y + (t % 3) * kT2;
-        const int pvalid = min(kT2, n_out - t * kT2);
-        const int pnev = B.n_ev[ps];
-        int n_closed = 0, c_kind[2] = {0, 0}, c_ord[2] = {0, 0}, c_open[2] = {0, 0};
-        int pos = 0;
-        for (int e = 0; e <= pnev; e++) {
-          const bool last = e == pnev;
-          const int etype = last ? 0 : B.ev[ps][e].type;
-          const int epos = last ? pvalid : B.ev[ps][e].pos;
-          if (f_open) {
-            const int take = epos - pos;
-            if (f_store && take > 0)
-              for (int j = lane; j < take; j += 32) win[f_wpos + j] = py[pos + j];
-            f_wpos += take;
-            pos = epos;
-          }
-          if (etype == 2) {
-            if (f_open && f_store && n_closed < 2) { c_kind[n_closed] = cur_kind; c_ord[n_closed] = cur_ordinal; c_open[n_closed] = cur_open_idx; n_closed++; }
-            f_open = false;
-            pos = epos;
-          } else if (etype == 1) {
-            f_store = B.ev[ps][e].c != 0;
-            f_open = true;
-            cur_kind = B.ev[ps][e].d;
-            cur_ordinal = wsig_ordinal++;
-            cur_open_idx = B.ev[ps][e].b;
-            win = win_base + (cur_kind ? A.rn16_pad : 0);
-            if (f_store && lane == 0) win[0] = py[epos];
-            f_wpos = 1;
-            pos = epos + 1;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&B.done);  // the ring reads above are complete
+        while (B.n_dc <= k) __nanosleep(200);   // dc_est of this window: two tiles after it opened
+        __threadfence_block();
+        const int qs = k & (kPQ - 1);
+        const int kind = B.q_kind[qs], ord = B.q_ord[qs], wopen = B.q_open[qs];
+        const float2 dc = B.dc_val[qs];
+        const int len = kind ? C.len_epc : C.len_rn16;
+        const WinSrc wv{y_seg, wopen, kYW - 1};
         PP_AT(1)
-        for (int k = 0; k < n_closed; k++) {
-          const int kind = c_kind[k], len = kind ? C.len_epc : C.len_rn16;
-          const float2* wv = win_base + (kind ? A.rn16_pad : 0);
-          // dc_est of this window: posted by warp B three steps after the window opened
-          mbar_wait_idle(&B.dc_rdy[kind], (kind ? n_dc[1] : n_dc[0]) & 1u, 200);
-          if (kind) n_dc[1]++; else n_dc[0]++;
-          const float2 dc = B.dc_val[kind];
-          WindowDecode wd;
+        WindowDecode wd;
 #ifdef RFID_B200_PHASE_PROFILE
-          decode_window_staged(C, kind, wv, len, dstage, A.dstage_samples, wd, nullptr, nullptr, dc, pp_log ? pp_log + (kind ? 60 : 61) * 8 : nullptr);
+        decode_window_staged(C, kind, wv, len, dstage, A.dstage_samples, wd, nullptr, nullptr, dc, pp_log ? pp_log + (kind ? 60 : 61) * 8 : nullptr);
 #else
-          decode_window_staged(C, kind, wv, len, dstage, A.dstage_samples, wd, nullptr, nullptr, dc);
+        decode_window_staged(C, kind, wv, len, dstage, A.dstage_samples, wd, nullptr, nullptr, dc);
 #endif
-          rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + c_ord[k];
-          if (lane == 0) store_result(dst, wd, seg + A.seg_base, c_ord[k], c_open[k], len, kind);
+        rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ord;
+        if (lane == 0) store_result(dst, wd, seg + A.seg_base, ord, wopen, len, kind);
 #ifndef RFID_B200_PHASE_PROFILE
-          if (A.window_tap) {
-            float2* tap = A.window_tap + ((size_t)(seg + A.seg_base) * A.max_windows + c_ord[k]) * C.len_epc;
-            for (int p2 = lane; p2 < len; p2 += 32) tap[p2] = c_sub(__ldcg(wv + p2), dc);
-          }
-#endif
-          __syncwarp();
+        if (A.window_tap) {
+          float2* tap = A.window_tap + ((size_t)(seg + A.seg_base) * A.max_windows + ord) * C.len_epc;
+          for (int p2 = lane; p2 < len; p2 += 32) tap[p2] = c_sub(__ldcg(wv.at(p2)), dc);
         }
+#endif
+        __syncwarp();
+        k++;
+        if (lane == 0) { __threadfence_block(); B.n_decoded = k; }   // warp A may reuse the window's history samples
         PP_AT(2)
       }
     }

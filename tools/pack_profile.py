@@ -24,17 +24,19 @@ torch.cuda.synchronize()
 rx.set_window_tap(tap)
 rx.decode_capture(cap["iq"], segs, 2)
 torch.cuda.synchronize()
-log = tap.view(torch.int64).cpu().numpy().reshape(-1)[: 256 * 8].reshape(256, 8)
+log = tap.view(torch.int64).cpu().numpy().reshape(-1)[: 320 * 8].reshape(320, 8)
 A, B, CH, C = log[0:64], log[64:128], log[128:192], log[192:256]
-steps = 14 + 3
-print("B sub-phases: step | Ydone  pre-masks  masks  fsm  rebuild  P3done")
+steps = 14 + 2
+print("B sub-phases: tile | avg ready  pre-masks  masks  fsm  rebuild  P3done")
 for i in range(steps):
     print("%3d | %7d %7d %7d %7d %7d %7d" % (i, B[i][1], B[i][4], B[i][5], B[i][6], B[i][7], B[i][2]))
-print("step | A: start blocksums |y|stored P1end | B: start Ydone P3done rung | chain: start Xdone done | C(tile=step): go copied decoded")
+print("tile | A0: start blocksums |y|stored P1end | A1: start P1end | B: start avg-ready P3done | chain: start inputs-ready done")
+A1 = log[256:320] if log.shape[0] >= 320 else A
 for i in range(steps):
-    print("%3d | %7d %7d %7d %7d | %7d %7d %7d %7d | %7d %7d %7d | %7d %7d %7d" %
-          (i, A[i][0], A[i][1], A[i][2], A[i][3], B[i][0], B[i][1], B[i][2], B[i][3], CH[i][0], CH[i][1], CH[i][2], C[i][0], C[i][1], C[i][2]))
-
+    print("%3d | %7d %7d %7d %7d | %7d %7d | %7d %7d %7d | %7d %7d %7d" %
+          (i, A[i][0], A[i][1], A[i][2], A[i][3], A1[i][0], A1[i][3], B[i][0], B[i][1], B[i][2], CH[i][0], CH[i][1], CH[i][2]))
+for k in range(2):
+    print("window %d: close seen %d, dc ready %d, decoded %d" % (k, C[k][0], C[k][1], C[k][2]))
 for name, d in (("EPC", C[60]), ("RN16", C[61])):
     print("%s decode of segment 0 (cycles): head+sync %d, period search %d, bit samples %d, bits+crc %d, total %d" %
           (name, d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[4] - d[0]))
