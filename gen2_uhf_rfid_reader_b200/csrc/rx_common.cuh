@@ -100,6 +100,10 @@ __device__ __forceinline__ float cabsf_ref(float re, float im)
   return __double2float_rn(__dsqrt_rn(s));
 }
 
+// rare paths kept out of the callers' instruction stream (the capture kernels are instruction-cache sensitive)
+__device__ __noinline__ float cabsf_ref_call(float re, float im) { return cabsf_ref(re, im); }
+__device__ __noinline__ float f_div_const_call(float x, float d, float c, int fast) { return f_div_const(x, d, c, fast); }
+
 // The same value without the branches of __dsqrt_rn, so that several evaluations interleave: s as above, one Newton step
 // on rsqrt.approx.f64 (relative error after the step < 2^-40), rounded to float.  That equals
 // (float)sqrt_rn(s) whenever the approximation is farther than its own error bound from every float rounding boundary
@@ -175,6 +179,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking test (try_wait may park the thread for a system-dependent time when the phase is not complete): for a
+// warp that watches more than one barrier
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");

@@ -320,6 +320,38 @@ __device__ __forceinline__ void stage_fill_norm(float* stage_m, const WinSrc gw,
   __syncwarp();
 }
 
+// Whole window present (nobody to wait for): optionally touch the span's cache lines (L2 -> this SM's L1, one load per
+// lane), then fill in rolled batches of four loads per lane through L1.  Small code, and one trip to L2 per fill.  The
+// window was written by this SM before the decode began; an SM's own stores keep its L1 coherent.
+template <bool NORM>
+__device__ __forceinline__ void stage_fill_l1(void* stage_v, const WinSrc gw, int lo, int count, int n_avail, float2 dc, bool touch)
+{
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  float sink = 0.0f;
+  if (touch) sink = l1_touch_span(gw, lo, count, n_avail);
+#pragma unroll 1
+  for (int p0 = 0; p0 < count; p0 += 128) {
+    float2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int p = p0 + 32 * k + lane, g = lo + p;
+      v[k] = (p < count && g >= 0 && g < n_avail) ? ld_ca_f2(gw.at(g)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int p = p0 + 32 * k + lane, g = lo + p;
+      const bool in = g >= 0 && g < n_avail;
+      if (p < count) {
+        if (NORM) reinterpret_cast<float*>(stage_v)[p] = in ? c_norm(c_sub(v[k], dc)) : 0.0f;
+        else reinterpret_cast<float2*>(stage_v)[p] = in ? c_sub(v[k], dc) : make_float2(0.f, 0.f);
+      }
+    }
+  }
+  asm volatile("" ::"f"(sink));
+  __syncwarp();
+}
+
 // ---- the staged decode as a resumable sequence of phases ---------------------------------------------------------------
 // head (tag_sync, h_est, tag_decoder_impl.cc:78-109) -> kSearchChunks chunks of the symbol-period search (:151-165) ->
 // finish (argmax, 128 bit decisions :171-191, CRC).  Each phase needs the window only up to a known position, so a
@@ -356,9 +388,10 @@ __device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, con
 {
   const int lane = threadIdx.x & 31;
   const float n = c.n_tag_bit_f;
-  const float half = f_div(n, 2.0f);
+  const float half = f_mul(n, 0.5f);   // (x / 2 == x * 0.5 exactly, every x)
   const int head = win_head_samples(c, kind, n_total, stage_cap);
-  stage_fill(stage, gw, 0, head, n_total, progress, dc);
+  if (progress) stage_fill(stage, gw, 0, head, n_total, progress, dc);
+  else stage_fill_l1<false>(stage, gw, 0, head, n_total, dc, true);
   // (whole window present: start the first search chunk's lines towards L1 now; it begins 6.5 symbols after the sync index)
   float sink = 0.0f;
   if (!progress && kind != RFID_B200_RN16) sink = l1_touch_span(gw, (int)(6.5f * n), 32 * 16, n_total);
@@ -366,9 +399,9 @@ __device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, con
   int best_i = 0x7fffffff;
   for (int i = lane; i < c.sync_range; i += 32) {
     float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
+#pragma unroll 2
     for (int j = 0; j < 2 * kTagPreambleBits; j++) {
-      int k = (int)f_add((float)i, f_div(f_mul((float)j, n), 2.0f));
+      int k = (int)f_add((float)i, f_mul(f_mul((float)j, n), 0.5f));
       float2 s = stage[k];
       float cr = (float)((kPreambleMask >> j) & 1u);
       float pr = f_sub(f_mul(s.x, cr), f_mul(s.y, 0.0f));
@@ -385,10 +418,10 @@ __device__ __forceinline__ void win_stream_head(const RxConfig& c, int kind, con
   if (best > 0.0f) { max_index = best_i; max_corr = best; }
   {
     int t1 = (int)f_add((float)max_index, half);
-    int t3 = (int)f_add((float)max_index, f_div(f_mul(3.0f, n), 2.0f));
-    int t6 = (int)f_add((float)max_index, f_div(f_mul(6.0f, n), 2.0f));
-    int t10 = (int)f_add((float)max_index, f_div(f_mul(10.0f, n), 2.0f));
-    int t11 = (int)f_add((float)max_index, f_div(f_mul(11.0f, n), 2.0f));
+    int t3 = (int)f_add((float)max_index, f_mul(f_mul(3.0f, n), 0.5f));
+    int t6 = (int)f_add((float)max_index, f_mul(f_mul(6.0f, n), 0.5f));
+    int t10 = (int)f_add((float)max_index, f_mul(f_mul(10.0f, n), 0.5f));
+    int t11 = (int)f_add((float)max_index, f_mul(f_mul(11.0f, n), 0.5f));
     float2 s = stage[max_index];
     s = c_add(s, stage[t1]);
     s = c_add(s, stage[t3]);
@@ -447,7 +480,7 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
 {
   const int lane = threadIdx.x & 31;
   const float n = c.n_tag_bit_f;
-  const float half = f_div(n, 2.0f);
+  const float half = f_mul(n, 0.5f);
   const int index = S.index;
   const float2 h = S.h;
   if (kind == RFID_B200_RN16) {
@@ -494,7 +527,7 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
     while (S.phase <= kSearchChunks) {
       const int i0 = kChunkSteps * (S.phase - 1);
       const int lo = (int)f_add(f_mul((float)i0, c.t_min), (float)index);
-      stage_fill_norm<true>(stage_m, gw, lo, span, n_avail, nullptr, dc);
+      stage_fill_l1<true>(stage_m, gw, lo, span, n_avail, dc, true);
       float sink = 0.0f;
       if (S.phase < kSearchChunks) sink = l1_touch_span(gw, (int)f_add(f_mul((float)(i0 + kChunkSteps), c.t_min), (float)index), span, n_avail);
       if (lane < 20) {

@@ -177,10 +177,10 @@ __device__ __forceinline__ int fsm_closed_run_lanes(unsigned ltw, unsigned gtw, 
   const int lim = nvalid - 1 - n_T1;  // rises at or above lim cannot open the gate within this tile
   if (lim > 0) {
     unsigned cand;
-    if (n_T1 + 1 >= 32) {
-      // A rise that opens the gate is followed by n_T1 + 1 >= 32 edge-free positions, so inside its own word it is the
-      // highest edge; the first edge of the words above it (suffix minimum over the lanes) decides.  At most
-      // nvalid / (n_T1 + 1) rises qualify, so the loop below runs once or twice.
+    {
+      // (host: n_T1 + 1 >= 32.)  A rise that opens the gate is followed by n_T1 + 1 >= 32 edge-free positions, so inside
+      // its own word it is the highest edge; the first edge of the words above it (suffix minimum over the lanes) decides.
+      // At most nvalid / (n_T1 + 1) rises qualify, so the loop below runs once or twice.
       const int hi = E ? 31 - __clz(E) : -1;
       const int fe = (own && E) ? base + __ffs(E) - 1 : 1024;
       int nx = __shfl_down_sync(FULL, fe, 1);
@@ -193,8 +193,6 @@ __device__ __forceinline__ int fsm_closed_run_lanes(unsigned ltw, unsigned gtw, 
       const int r = base + hi;
       const bool q = own && hi >= 0 && ((RS >> hi) & 1u) && r < lim && nx > r + 1 + n_T1;
       cand = q ? (1u << hi) : 0u;
-    } else {
-      cand = RS & m_below(lim - base);
     }
     while (true) {
       const int r = first_of(cand);
@@ -357,7 +355,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                 x[2 * j] = make_float2(v.x, v.y);
                 x[2 * j + 1] = make_float2(v.z, v.w);
               }
-            } else {
+            } else {   // (first half-tile of a segment, odd offsets: one pass in 28 at most)
 #pragma unroll
               for (int j = 0; j < 2 * DECIM; j++) {
                 const bool before = (k == 0) && (DECIM * (t0 + h) - (DECIM - 1) + j < 0);  // before sample 0 of the segment: +0
@@ -424,7 +422,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           }
           if (__any_sync(0xffffffffu, risky)) {  // rare (about one tile in 60): the exact evaluation for the whole warp
 #pragma unroll
-            for (int q = 0; q < Q; q++) a[q] = cabsf_ref(y[q].x, y[q].y);
+            for (int q = 0; q < Q; q++) a[q] = cabsf_ref_call(y[q].x, y[q].y);
           }
           const int by = (i & 1) * kT2 + h2 * kTT, ba = (i % kPAS) * kT2 + h2 * kTT;   // this half-tile's place in the rings
           {
@@ -445,7 +443,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           int ia = ba + t0 - C.win_length, iy = by + t0 - C.dc_length;
           if (ia < 0) ia += kRingA;
           if (iy < 0) iy += kRingY;
-          if (((C.win_length | C.dc_length) & 3) == 0) {  // lookback groups are aligned and never straddle the ring's end
+          {  // (host: window / DC lengths are multiples of 4, so the lookback groups are aligned and never straddle a ring's end)
             const float4 oa = *reinterpret_cast<const float4*>(ring_a + ia);
             xd[0] = f_sub(a[0], oa.x); xd[1] = f_sub(a[1], oa.y); xd[2] = f_sub(a[2], oa.z); xd[3] = f_sub(a[3], oa.w);
 #pragma unroll
@@ -453,17 +451,6 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
               const float4 oy = *reinterpret_cast<const float4*>(ring_y + iy + q);
               xr[q] = f_sub(y[q].x, oy.x); xi[q] = f_sub(y[q].y, oy.y);
               xr[q + 1] = f_sub(y[q + 1].x, oy.z); xi[q + 1] = f_sub(y[q + 1].y, oy.w);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < Q; q++) {
-              int ja = ia + q, jy = iy + q;
-              if (ja >= kRingA) ja -= kRingA;
-              if (jy >= kRingY) jy -= kRingY;
-              const float2 old = ring_y[jy];
-              xd[q] = f_sub(a[q], ring_a[ja]);
-              xr[q] = f_sub(y[q].x, old.x);
-              xi[q] = f_sub(y[q].y, old.y);
             }
           }
           if (nvalid < kTT) {
@@ -493,9 +480,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           } else {  // an exact zero, a denormal, or an unverified divisor somewhere in the warp: IEEE division
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-              qd[q] = f_div_const(xd[q], winlen_f, C.win_recip, C.win_div_fast);
-              qr[q] = f_div_const(xr[q], dclen_f, C.dc_recip, C.dc_div_fast);
-              qi[q] = f_div_const(xi[q], dclen_f, C.dc_recip, C.dc_div_fast);
+              qd[q] = f_div_const_call(xd[q], winlen_f, C.win_recip, C.win_div_fast);
+              qr[q] = f_div_const_call(xr[q], dclen_f, C.dc_recip, C.dc_div_fast);
+              qi[q] = f_div_const_call(xi[q], dclen_f, C.dc_recip, C.dc_div_fast);
             }
           }
           if (nvalid < kTT) {
@@ -646,8 +633,8 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                         qr = f_div_fast(xr, dclen_f, C.dc_recip);
                         qi = f_div_fast(xi, dclen_f, C.dc_recip);
                       } else {
-                        qr = f_div_const(xr, dclen_f, C.dc_recip, C.dc_div_fast);
-                        qi = f_div_const(xi, dclen_f, C.dc_recip, C.dc_div_fast);
+                        qr = f_div_const_call(xr, dclen_f, C.dc_recip, C.dc_div_fast);
+                        qi = f_div_const_call(xi, dclen_f, C.dc_recip, C.dc_div_fast);
                       }
                       if (valid) { er[run_start + j] = qr; ei[run_start + j] = qi; }
                     }
@@ -734,33 +721,43 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
 #ifdef RFID_B200_PHASE_PROFILE
     if (blockIdx.x == 0 && A.window_tap) pp_log = reinterpret_cast<long long*>(A.window_tap) + 128 * 8;
 #endif
-    for (int i = 0; i < max_tiles + 2; i++) {
-#ifdef RFID_B200_PHASE_PROFILE
-      pp_step = i;
-#endif
+    // avg_ampl of tile ia as soon as every segment's P1(ia) is in, dc_est of tile id as soon as every segment's P3(id) has
+    // fixed its list -- whichever is ready, both in ONE convergent loop when both are
+    int ia = 0, id = 0;
+    while (ia < max_tiles || id < max_tiles) {
       PP_AT(0)
-      const int t = i - 2;
-      if (i < max_tiles) pwait(&cta.fullA[i % kPAS], (uint32_t)((i / kPAS) & 1));          // P1(i) of every segment
-      if (t >= 0) pwait(&cta.p3done[t & (kPDS - 1)], (uint32_t)((t >> 2) & 1));             // P3(i-2) of every segment
+      bool ra = false, rd = false;
+      while (true) {
+        ra = ia < max_tiles && mbar_test_wait(&cta.fullA[ia % kPAS], (uint32_t)((ia / kPAS) & 1));
+        rd = id < ia && mbar_test_wait(&cta.p3done[id & (kPDS - 1)], (uint32_t)((id >> 2) & 1));
+        if (ra || rd) break;
+        __nanosleep(20);
+      }
+#ifdef RFID_B200_PHASE_PROFILE
+      pp_step = ra ? ia : 32 + id;
+#endif
       PP_AT(1)
       {
-        // branch-free selection of this lane's buffer and length, then ONE convergent loop for all 24 chains
-        const int n_avg = i < max_tiles ? min(kT2, max(0, n_out - i * kT2)) : 0;
-        const int n_dc = (active && comp > 0 && t >= 0) ? ctl_all[g].n_e[t & (kPDS - 1)] : 0;
+        // branch-free selection of this lane's buffer and length
+        const int n_avg = ra ? min(kT2, max(0, n_out - ia * kT2)) : 0;
+        const int n_dc = (rd && active && comp > 0) ? ctl_all[g].n_e[id & (kPDS - 1)] : 0;
         const int n = active ? (comp == 0 ? n_avg : n_dc) : 0;
-        const int ofsA = ((i % kPAS) * G + g) * kPChainBuf;
-        const int ofsD = (((t & (kPDS - 1)) * 2 + (comp - 1)) * G + g) * kPChainBuf;
-        float* buf = comp == 0 ? dA + ofsA : dD + (active && comp > 0 ? ofsD : 0);
+        const int ofsA = ((ia % kPAS) * G + g) * kPChainBuf;
+        const int ofsD = (((id & (kPDS - 1)) * 2 + (comp - 1)) * G + g) * kPChainBuf;
+        float* buf = comp == 0 ? dA + (ia < max_tiles ? ofsA : 0) : dD + (active && comp > 0 && id < max_tiles ? ofsD : 0);
         const int n16 = (n + 15) & ~15;
         __syncwarp();
         chain_inplace(buf, n16, acc);
         __syncwarp();
-        if (i < max_tiles && lane == 0) mbar_arrive(&cta.avgdone[i % kPAS]);
-        // ---- dc_est right after the trigger sample of every queued window that opened in tile t: hand it to warp C
-        if (t >= 0) {
+        if (ra) {
+          if (lane == 0) mbar_arrive(&cta.avgdone[ia % kPAS]);
+          ia++;
+        }
+        // ---- dc_est right after the trigger sample of every queued window that opened in tile id: hand it to warp C
+        if (rd) {
           if (active && comp > 0) {
             PackSegCtl& S = ctl_all[g];
-            const int s = t & (kPDS - 1);
+            const int s = id & (kPDS - 1);
             const int tn = S.trig_n[s];
             for (int e = 0; e < tn; e++) {
               const float v = buf[S.trig_j[s][e]];
@@ -771,11 +768,12 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           __syncwarp();
           if (active && comp == 1) {
             PackSegCtl& S = ctl_all[g];
-            const int tn = S.trig_n[t & (kPDS - 1)];
+            const int tn = S.trig_n[id & (kPDS - 1)];
             if (tn > 0) { __threadfence_block(); S.n_dc = S.n_dc + tn; }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&cta.dcdone[t & (kPDS - 1)]);
+          if (lane == 0) mbar_arrive(&cta.dcdone[id & (kPDS - 1)]);
+          id++;
         }
       }
       PP_AT(2)
