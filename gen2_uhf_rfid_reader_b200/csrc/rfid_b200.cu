@@ -208,7 +208,7 @@ __global__ void query_nsmid_kernel(unsigned* out)
 bool pack_ok(const RxConfig& c)
 {
   return c.decim == 5 && c.mf_rem == 0 && c.mf_q == 5 && fast_path_ok(c) && c.len_rn16 >= kT2 / 2 &&
-         c.len_epc + c.dc_length + 8 * kT2 <= kYW && ((c.win_length | c.dc_length) & 3) == 0 && c.n_T1 + 1 >= 32;
+         c.len_epc + c.dc_length + 8 * kT2 <= kYW && ((c.win_length | c.dc_length) & 3) == 0 && c.dc_length <= 124 && c.win_length <= kT2 && c.n_T1 + 1 >= 32;
 }
 
 // shared-memory carve-up of rx_pack_kernel for G segments per CTA
@@ -218,10 +218,17 @@ void make_layout_pack(const RxConfig& c, int G, PackArgs& L)
   L.raw_stage_samples = c.decim * kTT + 2;
   int o = 0;
   L.o_raw = o; o = align_up(o + 2 * L.raw_stage_samples * 8, 16);
-  L.o_ring_y = o; o += kRingY * 8;
+  L.o_tail_y = o; o = align_up(o + 2 * c.dc_length * 8, 16);
   L.o_ring_a = o; o += kRingA * 4;
-  L.dstage_samples = decode_stage_samples(c.n_tag_bit_f);
-  if (L.dstage_samples < c.len_rn16) L.dstage_samples = align_up(c.len_rn16, 8);  // an RN16 window is staged whole
+  // decode stage: an RN16 window is staged whole; an EPC window needs its head (sync range + 6 symbols) and one chunk of
+  // the symbol-period search (one float per sample) -- the bit decisions read the history directly
+  {
+    const int head = c.sync_range + (int)(6.0f * c.n_tag_bit_f) + 2;
+    const int span = (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8;
+    int need = c.len_rn16 > head ? c.len_rn16 : head;
+    if (need < (span + 1) / 2) need = (span + 1) / 2;
+    L.dstage_samples = align_up(need, 8);
+  }
   L.o_dstage = o; o = align_up(o + L.dstage_samples * 8, 16);
   L.seg_bytes = o;
   int off = 0;

@@ -524,6 +524,51 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
     // instructions, but slower than the plain loop below: 19.6 k vs 15.6 k cycles per window.)
     float* stage_m = reinterpret_cast<float*>(stage);
     const int span = min(2 * stage_cap, (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
+    if (span <= 32 * kFillBatch) {
+      // chunk k+1's samples travel from L2 into registers while chunk k's 64 steps run from the stage
+      float2 v[kFillBatch];
+      int lo = (int)f_add(f_mul((float)(kChunkSteps * (S.phase - 1)), c.t_min), (float)index);
+      auto issue = [&](int lo_) {
+#pragma unroll
+        for (int k = 0; k < kFillBatch; k++) {
+          const int p = 32 * k + lane, g = lo_ + p;
+          v[k] = (p < span && g >= 0 && g < n_avail) ? __ldcg(gw.at(g)) : make_float2(0.f, 0.f);
+        }
+      };
+      issue(lo);
+      while (S.phase <= kSearchChunks) {
+        const int i0 = kChunkSteps * (S.phase - 1);
+        __syncwarp();  // the previous chunk's reads of the stage are complete
+#pragma unroll
+        for (int k = 0; k < kFillBatch; k++) {
+          const int p = 32 * k + lane, g = lo + p;
+          if (p < span) stage_m[p] = (g >= 0 && g < n_avail) ? c_norm(c_sub(v[k], dc)) : 0.0f;
+        }
+        __syncwarp();
+        const float* sm = stage_m - lo;
+        if (S.phase < kSearchChunks) {
+          lo = (int)f_add(f_mul((float)(i0 + kChunkSteps), c.t_min), (float)index);
+          issue(lo);
+        }
+        if (lane < 20) {
+          const float findex = (float)index, Tt = S.Tt;
+          float e = S.e;
+#pragma unroll 1
+          for (int i = i0; i < i0 + kChunkSteps; i += 16) {
+            // sixteen gathers in flight, then their sixteen additions in order
+            const float fi = (float)i;
+            float u16[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) u16[u] = sm[(int)f_add(f_mul(f_add(fi, (float)u), Tt), findex)];  // (int)(i * T + index), :161
+#pragma unroll
+            for (int u = 0; u < 16; u++) e = f_add(e, u16[u]);
+          }
+          S.e = e;
+        }
+        S.phase++;
+      }
+      __syncwarp();
+    } else {
     while (S.phase <= kSearchChunks) {
       const int i0 = kChunkSteps * (S.phase - 1);
       const int lo = (int)f_add(f_mul((float)i0, c.t_min), (float)index);
@@ -532,18 +577,22 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
       if (S.phase < kSearchChunks) sink = l1_touch_span(gw, (int)f_add(f_mul((float)(i0 + kChunkSteps), c.t_min), (float)index), span, n_avail);
       if (lane < 20) {
         const float findex = (float)index, Tt = S.Tt;
-        float fi = (float)i0;
+        const float* sm = stage_m - lo;
         float e = S.e;
-#pragma unroll 8
-        for (int i = i0; i < i0 + kChunkSteps; i++) {
-          const int p = (int)f_add(f_mul(fi, Tt), findex);  // (int)(i * T + index), :161; fi == (float)i exactly
-          e = f_add(e, stage_m[p - lo]);
-          fi = f_add(fi, 1.0f);
+#pragma unroll 1
+        for (int i = i0; i < i0 + kChunkSteps; i += 16) {
+          const float fi = (float)i;
+          float v[16];
+#pragma unroll
+          for (int u = 0; u < 16; u++) v[u] = sm[(int)f_add(f_mul(f_add(fi, (float)u), Tt), findex)];  // (int)(i * T + index), :161
+#pragma unroll
+          for (int u = 0; u < 16; u++) e = f_add(e, v[u]);
         }
         S.e = e;
       }
       asm volatile("" ::"f"(sink));  // the touch may complete any time before here
       S.phase++;
+    }
     }
   } else {
     while (S.phase <= kSearchChunks) win_stream_chunk(c, gw, n_avail, stage, stage_cap, dc, S, progress);

@@ -25,9 +25,9 @@
 //   loader      lane g streams segment g's raw samples through its two half-tile stages as warp A frees them.
 // The history is indexed by the SM (one CTA per SM: the shared-memory request guarantees it), so its size does not depend
 // on the number of segments of the launch; warp A never overwrites a sample a queued window still needs.
-// Shared memory per segment: 2 raw half-tile stages (10 KB), warp A's own 2-tile time ring of y (4 KB), a 3-tile ring of
-// |y| (3 KB); per CTA the running-sum buffers (3 + 4x2 per segment, 1072 B each, skewed so the chain warp's 128-bit
-// accesses are bank-conflict free).  HBM traffic: every raw sample is read once, 64 B are written per window; the history
+// Shared memory per segment: 2 raw half-tile stages (10 KB), the last dc_length outputs of either half-tile (P1's DC lookback
+// is a lane shuffle plus this tail), a 4-tile ring of |y| (4 KB); per CTA the running-sum buffers (4 + 5x2 per segment,
+// 1072 B each, skewed so the chain warp's 128-bit accesses are bank-conflict free).  HBM traffic: every raw sample is read once, 64 B are written per window; the history
 // (8 B per decimated sample, rewritten in place) lives in L2.
 #pragma once
 
@@ -36,10 +36,9 @@
 namespace rfid_b200 {
 
 constexpr int kT2 = 2 * kTT;                 // decimated samples per tile (two half-tiles of kTT)
-constexpr int kRingY = 2 * kT2;              // warp A's time ring of y: tile t and t-1 (DC lookback of P1)
-constexpr int kPAS = 3;                      // slots of the |y| ring and of the amplitude quotient / avg_ampl lists
+constexpr int kPAS = 4;                      // slots of the |y| ring and of the amplitude quotient / avg_ampl lists
 constexpr int kRingA = kPAS * kT2;
-constexpr int kPDS = 4;                      // DC-list slots: P1 up to three tiles ahead, P3 fix-ups, chain
+constexpr int kPDS = 5;                      // DC-list slots: P1 up to four tiles ahead, P3 fix-ups, chain
 constexpr int kPMaxSeg = 7;                  // segments per CTA (chain lanes 8*c + g, g < 8)
 constexpr int kPChainBuf = kT2 + 12;         // floats per running-sum buffer: read-ahead pad; 1072 B = 48 mod 128
 constexpr int kPackMaxThreads = 32 * (4 * kPMaxSeg + 2);   // A0, A1, B, C per segment + loader + chain
@@ -63,7 +62,7 @@ struct PackArgs {
   int G;                                     // segments per CTA of this launch
   int raw_stage_samples;
   int seg_bytes;                             // per-segment shared-memory region
-  int o_raw, o_ring_y, o_ring_a, o_dstage;   // offsets inside a segment region
+  int o_raw, o_tail_y, o_ring_a, o_dstage;   // offsets inside a segment region
   int dstage_samples;
   int off_dA, off_dD, off_seg;               // offsets from the dynamic shared-memory base
   int smem_bytes;
@@ -79,9 +78,10 @@ struct PackSegCtl {
   // windows that will be decoded, by sequence number k (slot k & (kPQ-1)): written by warp B, dc_val by the chain warp
   int q_open[kPQ], q_kind[kPQ], q_ord[kPQ];
   float2 dc_val[kPQ];
-  volatile int n_opened, n_closed, n_dc, n_decoded, seg_done;
+  volatile int n_opened, n_dc, n_decoded, seg_done;
+  volatile int y_tiles;      // tiles whose y is complete in the history (written by warp A1, or A0 for a lone first half)
   // warp B's state that only changes at gate events (kept out of its registers)
-  int b_wcount, b_store, b_nq, b_snap_base, b_queued, b_closed;
+  int b_wcount, b_nq, b_snap_base, b_queued;
   int n_e[kPDS];             // closed samples of the tile in DC-list slot (written by P3)
   int trig_n[kPDS];          // queued windows that opened in that tile: index of the trigger in the list, sequence number
   int trig_j[kPDS][kPTrig], trig_k[kPDS][kPTrig];
@@ -108,13 +108,15 @@ __device__ __forceinline__ void pwait(uint64_t* bar, uint32_t parity) { mbar_wai
 // ---- the edge / pulse state machine of one closed run on 256-bit masks, the eight mask words spread over lanes 0..7 ----
 // Same decisions as fsm_closed_run (rx_fused_split.cuh) and therefore as the reference's sample loop
 // (gate_impl.cc:145-180):
-//   states     state' = rise | keep & state is the carry recurrence of a binary addition; across the words by carry
-//              look-ahead (both sums per word, a select chain over two ballots)
+//   states     state' = rise | keep & state is the carry recurrence of a binary addition; inside a word one 64-bit add,
+//              across the words the same recurrence once more (generate = the word's sum overflows with carry-in 0,
+//              propagate = only with carry-in 1), i.e. one more addition on the two ballots
 //   pulses     a rise at p is a valid pulse when the fall before it is more than half_pw back: no fall bit at p-1 .. p-half_pw
 //   num_pulses valid rises since the last invalid one (plus the carried count while no invalid rise has occurred)
 //   opening    the carried state reaches T1 before the first edge, or a rise r with num_pulses > 5 is followed by
 //              n_T1 + 1 edge-free samples inside the tile (gate opens at r + 1 + n_T1; a fall there wins)
-// Positions and counts are combined with redux.sync / vote (one instruction each).
+// Positions and counts are combined with redux.sync / vote (one instruction each); the reductions of the common path
+// (a tile full of reader pulses, no opening) do not depend on each other, so they are in flight together.
 struct GateFsm2 {
   bool sig_pos;
   int n_samples, num_pulses;
@@ -130,23 +132,19 @@ __device__ __forceinline__ int fsm_closed_run_lanes(unsigned ltw, unsigned gtw, 
   const int w = lane & 7;
   const bool own = lane < 8;
   const int base = 32 * w;
-  const unsigned live = ~m_below(from - base);
+  const unsigned live = own ? ~m_below(from - base) : 0u;   // (lanes 8..31 carry empty words)
   const unsigned F = ltw & live, R = gtw & live;
   const unsigned Pk = ~(F | R);
   const unsigned long long sum0 = (unsigned long long)(R | Pk) + R, sum1 = sum0 + 1ull;
-  const unsigned C0 = __ballot_sync(FULL, own && (sum0 >> 32) != 0ull), C1 = __ballot_sync(FULL, own && (sum1 >> 32) != 0ull);
-  unsigned cin = st.sig_pos ? 1u : 0u, cw = cin;
-#pragma unroll
-  for (int k = 0; k < 7; k++) {            // carry into word k+1
-    cin = cin ? ((C1 >> k) & 1u) : ((C0 >> k) & 1u);
-    cw = w == k + 1 ? cin : cw;
-  }
-  const unsigned X = Pk ^ (unsigned)(cw ? sum1 : sum0);   // state before each position
+  const unsigned C0 = __ballot_sync(FULL, own && (sum0 >> 32) != 0ull) & 0xffu;
+  const unsigned C1 = __ballot_sync(FULL, own && (sum1 >> 32) != 0ull) & 0xffu;
+  const unsigned cv = (C1 + C0 + (st.sig_pos ? 1u : 0u)) ^ C1 ^ C0;   // bit k: carry into word k (C0 is a subset of C1)
+  const unsigned X = Pk ^ (unsigned)(((cv >> w) & 1u) ? sum1 : sum0);   // state before each position
   const unsigned RS = ~X & R, FE = X & F, E = RS | FE;
-  auto first_of = [&](unsigned m) { return __reduce_min_sync(FULL, (own && m) ? base + __ffs(m) - 1 : 1024); };
-  auto last_of = [&](unsigned m) { return __reduce_max_sync(FULL, (own && m) ? base + 31 - __clz(m) : -1); };
-  auto bit_at = [&](unsigned m, int p) { return __any_sync(FULL, own && (p >> 5) == w && ((m >> (p & 31)) & 1u)); };
-  const int e_first = first_of(E);
+  const int e_first = __reduce_min_sync(FULL, E ? base + __ffs(E) - 1 : 1024);
+  const int e_last = __reduce_max_sync(FULL, E ? base + 31 - __clz(E) : -1);
+  const int r_last = __reduce_max_sync(FULL, RS ? base + 31 - __clz(RS) : -1);
+  const unsigned fe_prev = __shfl_up_sync(FULL, FE, 1);
   const int first_edge = e_first < nvalid ? e_first : nvalid;
   if (st.sig_pos && st.num_pulses > kNumPulsesCommand) {
     const int p_open = from + max(0, n_T1 - st.n_samples);
@@ -156,60 +154,68 @@ __device__ __forceinline__ int fsm_closed_run_lanes(unsigned ltw, unsigned gtw, 
     }
   }
   if (e_first >= nvalid) { st.n_samples += nvalid - from; return -1; }
-  const unsigned fe_prev = __shfl_up_sync(FULL, FE, 1);
   const unsigned fe_lo = w == 0 ? 0u : fe_prev;
   unsigned knock = 0u;
   for (int k = 1; k <= half_pw; k++) knock |= (FE << k) | (fe_lo >> (32 - k));
   unsigned VR = RS & ~knock;
-  if (bit_at(RS, e_first)) {
-    const bool valid = st.n_samples + (e_first - from + 1) > half_pw;   // the pulse began before the run
-    if (!valid && (e_first >> 5) == w) VR &= ~(1u << (e_first & 31));
-  }
+  // the first edge, if it is a rise: its pulse began before the run
+  if ((e_first >> 5) == w && ((RS >> (e_first & 31)) & 1u) && !(st.n_samples + (e_first - from + 1) > half_pw))
+    VR &= ~(1u << (e_first & 31));
   const unsigned IR = RS & ~VR;
   const int np_in = st.num_pulses;
-  auto np_at = [&](int r) {  // num_pulses right after the rise at r
-    const unsigned upto = m_below(r + 1 - base);
-    const int last = last_of(IR & upto);
-    const unsigned rng = upto & ~m_below(last + 1 - base);
-    const int cnt = __reduce_add_sync(FULL, own ? __popc(VR & rng) : 0);
-    return last >= 0 ? cnt : np_in + cnt;
-  };
   const int lim = nvalid - 1 - n_T1;  // rises at or above lim cannot open the gate within this tile
-  if (lim > 0) {
-    unsigned cand;
+  // (host: n_T1 + 1 >= 32.)  A rise that opens the gate is followed by n_T1 + 1 edge-free positions; when that is 64 or
+  // more, the stretch covers a whole mask word, so a tile without an edge-free word below nvalid has no candidate.
+  if (lim > 0 && (n_T1 + 1 < 64 || __any_sync(FULL, own && base < nvalid && E == 0u))) {
+    auto first_of = [&](unsigned m) { return __reduce_min_sync(FULL, m ? base + __ffs(m) - 1 : 1024); };
+    auto last_of = [&](unsigned m) { return __reduce_max_sync(FULL, m ? base + 31 - __clz(m) : -1); };
+    auto np_at = [&](int r) {  // num_pulses right after the rise at r
+      const unsigned upto = m_below(r + 1 - base);
+      const int last = last_of(IR & upto);
+      const unsigned rng = upto & ~m_below(last + 1 - base);
+      const int cnt = __reduce_add_sync(FULL, __popc(VR & rng));
+      return last >= 0 ? cnt : np_in + cnt;
+    };
+    // inside its own word an opening rise is the highest edge; the first edge of the words above it (suffix minimum over
+    // the lanes) decides.  At most nvalid / (n_T1 + 1) rises qualify, so the loop below runs once or twice.
+    const int hi = E ? 31 - __clz(E) : -1;
+    const int fe = E ? base + __ffs(E) - 1 : 1024;
+    int nx = __shfl_down_sync(FULL, fe, 1);
+    if (w == 7) nx = 1024;
     {
-      // (host: n_T1 + 1 >= 32.)  A rise that opens the gate is followed by n_T1 + 1 >= 32 edge-free positions, so inside
-      // its own word it is the highest edge; the first edge of the words above it (suffix minimum over the lanes) decides.
-      // At most nvalid / (n_T1 + 1) rises qualify, so the loop below runs once or twice.
-      const int hi = E ? 31 - __clz(E) : -1;
-      const int fe = (own && E) ? base + __ffs(E) - 1 : 1024;
-      int nx = __shfl_down_sync(FULL, fe, 1);
-      if (w == 7) nx = 1024;
-      {
-        int t1 = __shfl_down_sync(FULL, nx, 1); if (w >= 6) t1 = 1024; nx = min(nx, t1);
-        int t2 = __shfl_down_sync(FULL, nx, 2); if (w >= 5) t2 = 1024; nx = min(nx, t2);
-        int t4 = __shfl_down_sync(FULL, nx, 4); if (w >= 3) t4 = 1024; nx = min(nx, t4);
-      }
-      const int r = base + hi;
-      const bool q = own && hi >= 0 && ((RS >> hi) & 1u) && r < lim && nx > r + 1 + n_T1;
-      cand = q ? (1u << hi) : 0u;
+      int t1 = __shfl_down_sync(FULL, nx, 1); if (w >= 6) t1 = 1024; nx = min(nx, t1);
+      int t2 = __shfl_down_sync(FULL, nx, 2); if (w >= 5) t2 = 1024; nx = min(nx, t2);
+      int t4 = __shfl_down_sync(FULL, nx, 4); if (w >= 3) t4 = 1024; nx = min(nx, t4);
     }
+    const int rr = base + hi;
+    const bool q = own && hi >= 0 && ((RS >> hi) & 1u) && rr < lim && nx > rr + 1 + n_T1;
+    unsigned cand = q ? (1u << hi) : 0u;
     while (true) {
       const int r = first_of(cand);
       if (r >= 1024) break;
-      if ((r >> 5) == w) cand &= ~(1u << (r & 31));
+      if (own && (r >> 5) == w) cand &= ~(1u << (r & 31));
       const unsigned quiet_rng = m_below(r + 2 + n_T1 - base) & ~m_below(r + 1 - base);
-      if (!__any_sync(FULL, own && (E & quiet_rng) != 0u) && np_at(r) > kNumPulsesCommand) {
+      if (!__any_sync(FULL, (E & quiet_rng) != 0u) && np_at(r) > kNumPulsesCommand) {
         st.sig_pos = true; st.num_pulses = 0; st.n_samples = 1;
         return r + 1 + n_T1;
       }
     }
   }
-  const int e_last = last_of(E);
-  st.sig_pos = bit_at(RS, e_last);
+  st.sig_pos = e_last == r_last;            // the last edge is a rise
   st.n_samples = nvalid - 1 - e_last;
-  const int r_last = last_of(RS);
-  if (r_last >= 0) st.num_pulses = np_at(r_last);
+  if (r_last >= 0) {
+    // valid rises after the last invalid one: the words above the last word that holds an invalid rise, and that word's
+    // bits above it
+    const unsigned Lm = __ballot_sync(FULL, IR != 0u) & 0xffu;
+    unsigned mine = VR;
+    if (Lm) {
+      const int L = 31 - __clz(Lm);
+      if (w < L) mine = 0u;
+      else if (w == L && IR) mine = VR & ~((2u << (31 - __clz(IR))) - 1u);
+    }
+    const int cnt = __reduce_add_sync(FULL, own ? __popc(mine) : 0);
+    st.num_pulses = Lm ? cnt : np_in + cnt;
+  }
   return -1;
 }
 
@@ -223,6 +229,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
   __shared__ long long pp_cta_t0;
   if (threadIdx.x == 0) pp_cta_t0 = clock64();
   int pp_step = 0;
+  // per-CTA start / end on the global timer (ns): rows 512.. of the log
+  unsigned long long* pp_cta = A.window_tap ? reinterpret_cast<unsigned long long*>(A.window_tap) + 512 * 8 + 2 * blockIdx.x : nullptr;
+  if (pp_cta && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); pp_cta[0] = t; }
 #endif
 
   static_assert(MFQ >= 2, "pack kernel: block-sum matched filter");
@@ -252,8 +261,8 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     for (int s = 0; s < kPAS; s++) mbar_init(&c.freeA[s], 1);
     for (int m = 0; m < 4; m++) { c.keep[0][m] = make_float2(0.f, 0.f); c.keep[1][m] = make_float2(0.f, 0.f); }
     for (int s = 0; s < kPDS; s++) { c.n_e[s] = 0; c.trig_n[s] = 0; }
-    c.n_opened = 0; c.n_closed = 0; c.n_dc = 0; c.n_decoded = 0; c.seg_done = 0;
-    c.b_wcount = 0; c.b_store = 0; c.b_nq = 1; c.b_snap_base = 0; c.b_queued = 0; c.b_closed = 0;
+    c.n_opened = 0; c.n_dc = 0; c.n_decoded = 0; c.seg_done = 0; c.y_tiles = 0;
+    c.b_wcount = 0; c.b_nq = 1; c.b_snap_base = 0; c.b_queued = 0;
   }
   if (threadIdx.x == 32) {
     for (int s = 0; s < kPAS; s++) { mbar_init(&cta.fullA[s], 2 * G); mbar_init(&cta.avgdone[s], 1); }
@@ -265,10 +274,10 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
   if (warp != 3 * G) {
     for (int g = 0; g < G; g++) {
       unsigned char* sb = smem + A.off_seg + (size_t)g * A.seg_bytes;
-      float4* ry = reinterpret_cast<float4*>(sb + A.o_ring_y);
+      float4* ry = reinterpret_cast<float4*>(sb + A.o_tail_y);
       float4* ra = reinterpret_cast<float4*>(sb + A.o_ring_a);
       const int tid = threadIdx.x - (warp > 3 * G ? 32 : 0), nth = blockDim.x - 32;
-      for (int i = tid; i < kRingY / 2; i += nth) ry[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < C.dc_length; i += nth) ry[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // two tails of dc_length samples
       for (int i = tid; i < kRingA / 4; i += nth) ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // the CTA's barriers count every warp A / B for every tile of the longest segment
@@ -294,11 +303,11 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     PackSegCtl& B = ctl_all[g];
     unsigned char* sb = smem + A.off_seg + (size_t)g * A.seg_bytes;
     float2* raw = reinterpret_cast<float2*>(sb + A.o_raw);
-    float2* ring_y = reinterpret_cast<float2*>(sb + A.o_ring_y);
+    float2* tail_y = reinterpret_cast<float2*>(sb + A.o_tail_y);   // [2][dc_length]: the last outputs of either half-tile
     float* ring_a = reinterpret_cast<float*>(sb + A.o_ring_a);
     float2* const y_seg = y_cta + (size_t)g * kYW;
     auto bufA = [&](int tile) { return dA + (size_t)((tile % kPAS) * G + g) * kPChainBuf; };
-    auto bufD = [&](int tile, int comp) { return dD + (size_t)(((tile & (kPDS - 1)) * 2 + comp) * G + g) * kPChainBuf; };
+    auto bufD = [&](int tile, int comp) { return dD + (size_t)(((tile % kPDS) * 2 + comp) * G + g) * kPChainBuf; };
     const float dclen_f = (float)C.dc_length;
     PP_DECL
 
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           // the slots this tile is written into are free: warp B made the masks of tile i-3, the chain warp is through
           // with the DC list of tile i-4, and no queued window still needs the history samples about to be replaced
           if (i >= kPAS) pwait(&B.freeA[i % kPAS], (uint32_t)((i / kPAS - 1) & 1));
-          if (i >= kPDS) pwait(&cta.dcdone[i & (kPDS - 1)], (uint32_t)(((i >> 2) - 1) & 1));
+          if (i >= kPDS) pwait(&cta.dcdone[i % kPDS], (uint32_t)((i / kPDS - 1) & 1));
           if ((i + 1) * kT2 > kYW) {
             const int lowest = (i + 1) * kT2 - kYW;     // oldest history sample that survives this tile
             while (true) {
@@ -424,33 +433,47 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
 #pragma unroll
             for (int q = 0; q < Q; q++) a[q] = cabsf_ref_call(y[q].x, y[q].y);
           }
-          const int by = (i & 1) * kT2 + h2 * kTT, ba = (i % kPAS) * kT2 + h2 * kTT;   // this half-tile's place in the rings
+          const int ba = (i % kPAS) * kT2 + h2 * kTT;   // this half-tile's place in the |y| ring
           {
             const float4 y01 = make_float4(y[0].x, y[0].y, y[1].x, y[1].y), y23 = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
-            float4* py = reinterpret_cast<float4*>(ring_y + by + t0);
-            py[0] = y01;
-            py[1] = y23;
             *reinterpret_cast<float4*>(ring_a + ba + t0) = make_float4(a[0], a[1], a[2], a[3]);
             float4* hy = reinterpret_cast<float4*>(y_seg + ((i * kT2 + h2 * kTT + t0) & (kYW - 1)));   // the history
             hy[0] = y01;
             hy[1] = y23;
           }
           PP_AT(2)
-          __syncwarp();  // this half-tile's |y| and y visible to the lookbacks below
+          __syncwarp();  // this half-tile's |y| visible to the lookback below
           if (h2 == 1) pwait(&B.half_rdy, (uint32_t)(i & 1));   // the lookbacks reach into the first half
-          // ---- ring differences (gate_impl.cc:131,141)
+          // ---- ring differences (gate_impl.cc:131,141).  |y| from the time ring; y from dc_length samples back: the lane
+          // dc_length / 4 below (same output slot), or -- for the first lanes -- the tail the previous half-tile left.
+          // (host: window / DC lengths are multiples of 4, so the groups are aligned and never straddle the ring's end)
           float xd[Q], xr[Q], xi[Q];
-          int ia = ba + t0 - C.win_length, iy = by + t0 - C.dc_length;
-          if (ia < 0) ia += kRingA;
-          if (iy < 0) iy += kRingY;
-          {  // (host: window / DC lengths are multiples of 4, so the lookback groups are aligned and never straddle a ring's end)
+          {
+            int ia = ba + t0 - C.win_length;
+            if (ia < 0) ia += kRingA;
             const float4 oa = *reinterpret_cast<const float4*>(ring_a + ia);
             xd[0] = f_sub(a[0], oa.x); xd[1] = f_sub(a[1], oa.y); xd[2] = f_sub(a[2], oa.z); xd[3] = f_sub(a[3], oa.w);
+            const int dl = C.dc_length >> 2;                                   // lanes
+            const float2* tprev = tail_y + (h2 ? 0 : C.dc_length);             // A0 reads A1's tail (previous tile), A1 reads A0's
+            float4 t01 = make_float4(0.f, 0.f, 0.f, 0.f), t23 = t01;
+            if (lane < dl) {
+              t01 = *reinterpret_cast<const float4*>(tprev + 4 * lane);
+              t23 = *reinterpret_cast<const float4*>(tprev + 4 * lane + 2);
+            }
+            float2 oy[Q];
 #pragma unroll
-            for (int q = 0; q < Q; q += 2) {
-              const float4 oy = *reinterpret_cast<const float4*>(ring_y + iy + q);
-              xr[q] = f_sub(y[q].x, oy.x); xi[q] = f_sub(y[q].y, oy.y);
-              xr[q + 1] = f_sub(y[q + 1].x, oy.z); xi[q + 1] = f_sub(y[q + 1].y, oy.w);
+            for (int q = 0; q < Q; q++) {
+              oy[q].x = __shfl_up_sync(0xffffffffu, y[q].x, dl);
+              oy[q].y = __shfl_up_sync(0xffffffffu, y[q].y, dl);
+            }
+            if (lane < dl) { oy[0] = make_float2(t01.x, t01.y); oy[1] = make_float2(t01.z, t01.w); oy[2] = make_float2(t23.x, t23.y); oy[3] = make_float2(t23.z, t23.w); }
+#pragma unroll
+            for (int q = 0; q < Q; q++) { xr[q] = f_sub(y[q].x, oy[q].x); xi[q] = f_sub(y[q].y, oy[q].y); }
+            // this half-tile's own tail (the previous reader of that buffer is through: tail_rdy / half_rdy above)
+            if (lane >= 32 - dl) {
+              float4* tw = reinterpret_cast<float4*>(tail_y + (h2 ? C.dc_length : 0) + 4 * (lane - (32 - dl)));
+              tw[0] = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
+              tw[1] = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
             }
           }
           if (nvalid < kTT) {
@@ -467,7 +490,8 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           }
           const bool all_ok = C.win_div_fast && C.dc_div_fast && mn >= kDivFastMin && mx <= kDivFastMax;
           const bool warp_ok = __all_sync(0xffffffffu, all_ok);
-          // (every lane's lookback values have arrived: warp A1 may go on to this tile's second half)
+          __syncwarp();
+          // (every lane's lookback values have arrived, this half's tail is written: warp A1 may go on to the second half)
           if (h2 == 0 && lane == 0 && (k + 1) * kTT < n_out) mbar_arrive(&B.half_rdy);
           float qd[Q], qr[Q], qi[Q];
           if (warp_ok) {
@@ -498,6 +522,8 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           __syncwarp();
           // second half-tile (and the halo) handed to warp A0's next tile
           if (h2 == 1 && lane == 0 && (k + 1) * kTT < n_out) mbar_arrive(&B.tail_rdy);
+          // the tile's y is in the history (warp A1 got here after warp A0's half_rdy; a lone first half is the segment's last)
+          if (lane == 0 && (h2 == 1 || (k + 1) * kTT >= n_out)) { __threadfence_block(); B.y_tiles = i + 1; }
         }
         PP_AT(3)
         __syncwarp();
@@ -531,7 +557,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           // room in the window queue for every window this tile can open (the oldest queued window has closed and its
           // dc_est is out or on its way: warp C does not depend on this warp to get through it)
           while (B.b_queued - B.n_decoded > kPQ - 1 - kPTrig) __nanosleep(200);
-          const int s = t & (kPDS - 1);
+          const int s = t % kPDS;
           int n_e = 0, ntrig = 0;
           const int nvalid = min(kT2, n_out - t * kT2);
           const int tb = t * kT2;                     // history index of the tile's first sample
@@ -647,11 +673,12 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                   // READER COMMAND DETECTED (gate_impl.cc:164-180): the DC ring stands as it is now
                   gate_open = true;
                   const int open_idx = tb + pos - 1, wcount = B.b_wcount, n_queued = B.b_queued;
-                  const bool cur_store = wcount < A.max_windows && ntrig < kPTrig;  // (windows beyond max_windows are not decoded)
+                  // a window is decoded when it closes inside the segment (its length is known now); windows beyond
+                  // max_windows are not decoded
+                  const bool cur_store = wcount < A.max_windows && ntrig < kPTrig && open_idx + to_ungate <= n_out;
                   __syncwarp();
                   if (lane == 0) {
                     B.b_snap_base = open_idx - C.dc_length + 1;
-                    B.b_store = cur_store ? 1 : 0;
                     if (cur_store) {
                       // queue the window for warp C; dc_est right after the trigger sample follows from the chain warp
                       const int qs = n_queued & (kPQ - 1);
@@ -674,14 +701,12 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                 n_e = pos;
                 if (n_samples >= to_ungate) {
                   gate_open = false;
-                  const int wcount = B.b_wcount, nq = B.b_nq, ncl = B.b_closed;
-                  const bool stored = B.b_store != 0;
+                  const int wcount = B.b_wcount, nq = B.b_nq;
                   const int kind = wcount & 1;  // windows alternate RN16, EPC
                   __syncwarp();
                   if (lane == 0) {
                     B.b_wcount = wcount + 1;
                     if (kind) B.b_nq = nq + 1;
-                    if (stored) { B.b_closed = ncl + 1; __threadfence_block(); B.n_closed = ncl + 1; }
                   }
                   __syncwarp();
                   closed_since = 0;
@@ -703,7 +728,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         }
         PP_AT(2)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&cta.p3done[t & (kPDS - 1)]);   // the tile's DC list is final
+        if (lane == 0) mbar_arrive(&cta.p3done[t % kPDS]);   // the tile's DC list is final
       }
       // ---- end of the segment
       if (have && lane == 0) A.counts[seg] = B.b_wcount;
@@ -729,7 +754,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       bool ra = false, rd = false;
       while (true) {
         ra = ia < max_tiles && mbar_test_wait(&cta.fullA[ia % kPAS], (uint32_t)((ia / kPAS) & 1));
-        rd = id < ia && mbar_test_wait(&cta.p3done[id & (kPDS - 1)], (uint32_t)((id >> 2) & 1));
+        rd = id < ia && mbar_test_wait(&cta.p3done[id % kPDS], (uint32_t)((id / kPDS) & 1));
         if (ra || rd) break;
         __nanosleep(20);
       }
@@ -740,10 +765,10 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       {
         // branch-free selection of this lane's buffer and length
         const int n_avg = ra ? min(kT2, max(0, n_out - ia * kT2)) : 0;
-        const int n_dc = (rd && active && comp > 0) ? ctl_all[g].n_e[id & (kPDS - 1)] : 0;
+        const int n_dc = (rd && active && comp > 0) ? ctl_all[g].n_e[id % kPDS] : 0;
         const int n = active ? (comp == 0 ? n_avg : n_dc) : 0;
         const int ofsA = ((ia % kPAS) * G + g) * kPChainBuf;
-        const int ofsD = (((id & (kPDS - 1)) * 2 + (comp - 1)) * G + g) * kPChainBuf;
+        const int ofsD = (((id % kPDS) * 2 + (comp - 1)) * G + g) * kPChainBuf;
         float* buf = comp == 0 ? dA + (ia < max_tiles ? ofsA : 0) : dD + (active && comp > 0 && id < max_tiles ? ofsD : 0);
         const int n16 = (n + 15) & ~15;
         __syncwarp();
@@ -757,7 +782,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         if (rd) {
           if (active && comp > 0) {
             PackSegCtl& S = ctl_all[g];
-            const int s = id & (kPDS - 1);
+            const int s = id % kPDS;
             const int tn = S.trig_n[s];
             for (int e = 0; e < tn; e++) {
               const float v = buf[S.trig_j[s][e]];
@@ -768,11 +793,11 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
           __syncwarp();
           if (active && comp == 1) {
             PackSegCtl& S = ctl_all[g];
-            const int tn = S.trig_n[id & (kPDS - 1)];
+            const int tn = S.trig_n[id % kPDS];
             if (tn > 0) { __threadfence_block(); S.n_dc = S.n_dc + tn; }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&cta.dcdone[id & (kPDS - 1)]);
+          if (lane == 0) mbar_arrive(&cta.dcdone[id % kPDS]);
           id++;
         }
       }
@@ -829,18 +854,25 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       if (seg == 0 && A.window_tap) pp_log = reinterpret_cast<long long*>(A.window_tap) + 192 * 8;
 #endif
       for (int k = 0;;) {
+        // the next queued window: decodable as soon as its last sample is in the history (warp A runs ahead of the gate)
+        // and dc_est right after its trigger sample has come from the chain warp (two tiles after the gate opened it)
         const int done = B.seg_done;   // (read before the counter: once set, the counter is final)
-        const int nc = B.n_closed;
-        if (nc <= k) {
+        const int no = B.n_opened;
+        if (no <= k) {
           if (done) break;
-          __nanosleep(400);            // nothing to do until warp B closes a window
+          __nanosleep(400);            // nothing to do until warp B opens a window
           continue;
         }
+        __threadfence_block();
 #ifdef RFID_B200_PHASE_PROFILE
         pp_step = k;
 #endif
         PP_AT(0)
-        while (B.n_dc <= k) __nanosleep(200);   // dc_est of this window: two tiles after it opened
+        {
+          const int qs0 = k & (kPQ - 1);
+          const int wend = B.q_open[qs0] + (B.q_kind[qs0] ? C.len_epc : C.len_rn16);
+          while (B.y_tiles * kT2 < wend || B.n_dc <= k) __nanosleep(200);
+        }
         __threadfence_block();
         const int qs = k & (kPQ - 1);
         const int kind = B.q_kind[qs], ord = B.q_ord[qs], wopen = B.q_open[qs];
@@ -867,6 +899,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         if (lane == 0) { __threadfence_block(); B.n_decoded = k; }   // warp A may reuse the window's history samples
         PP_AT(2)
       }
+#ifdef RFID_B200_PHASE_PROFILE
+      if (pp_cta && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(pp_cta + 1, t); }
+#endif
     }
   }
 }

@@ -24,7 +24,16 @@ torch.cuda.synchronize()
 rx.set_window_tap(tap)
 rx.decode_capture(cap["iq"], segs, 2)
 torch.cuda.synchronize()
-log = tap.view(torch.int64).cpu().numpy().reshape(-1)[: 320 * 8].reshape(320, 8)
+raw_log = tap.view(torch.int64).cpu().numpy().reshape(-1)
+log = raw_log[: 320 * 8].reshape(320, 8)
+ncta = (nseg + 6) // 7
+ct = raw_log[512 * 8: 512 * 8 + 2 * ncta].reshape(ncta, 2).astype(np.float64)
+t0 = ct[:, 0].min()
+st, en = (ct[:, 0] - t0) / 1000.0, (ct[:, 1] - t0) / 1000.0
+print("CTAs %d: start us min %.2f max %.2f | last decode done us: min %.2f p50 %.2f p90 %.2f max %.2f | CTA 0: %.2f .. %.2f" %
+      (ncta, st.min(), st.max(), en.min(), np.percentile(en, 50), np.percentile(en, 90), en.max(), st[0], en[0]))
+order = np.argsort(en)
+print("slowest CTAs:", [(int(i), round(float(en[i]), 2)) for i in order[-6:]], "fastest:", [(int(i), round(float(en[i]), 2)) for i in order[:4]])
 A, B, CH, C = log[0:64], log[64:128], log[128:192], log[192:256]
 steps = 14 + 2
 print("B sub-phases: tile | avg ready  pre-masks  masks  fsm  rebuild  P3done")
