@@ -537,6 +537,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       bool gate_open = false;
       int to_ungate = C.len_rn16;
       bool terminated = false;
+      bool was_quiet = true;      // the last tile with a closed run had no sample below its threshold
       int closed_since = C.dc_length;
       // (window count, queries, queue counters, ...: PackSegCtl::b_*, touched at gate events only.  b_snap_base = history
       // index of the DC ring's oldest entry when the last window opened)
@@ -577,8 +578,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
             // thresholds (gate_impl.cc:136,148,154).  First a one-vote test in the lanes' natural 4-sample groups: while the
             // signal is high and no sample of the tile falls below its threshold, no edge can occur (carrier only).
             unsigned ltw = 0u, gtw = 0u;   // word (lane & 7) of the below- / above-threshold masks
+            // (only tried when the previous tile was edge-free too: inside a reader command the test would fail every time)
             bool quiet = false;
-            if (sig_pos && !gate_open && nvalid == kT2) {
+            if (sig_pos && !gate_open && nvalid == kT2 && was_quiet) {
               bool below = false;
 #pragma unroll
               for (int h2 = 0; h2 < 2; h2++) {
@@ -616,7 +618,9 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
                 PP_AT(4)
                 if (!have_masks && !(quiet && run_start == 0)) make_masks();
                 PP_AT(5)
-                if (sig_pos && !__any_sync(0xffffffffu, ltw != 0u)) {
+                const bool no_lt = !__any_sync(0xffffffffu, ltw != 0u);
+                was_quiet = no_lt;
+                if (sig_pos && no_lt) {
                   // carrier only (the common case): no falling edge can occur, only the open test remains
                   if (num_pulses > kNumPulsesCommand) {
                     const int cand = run_start + max(0, C.n_T1 - n_samples);
