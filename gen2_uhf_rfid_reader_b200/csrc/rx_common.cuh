@@ -250,6 +250,21 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// same, with an L2 eviction hint for data that is read exactly once (the raw capture): evict-first keeps the streaming
+// input from displacing the kernel's L2-resident scratch
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, unsigned long long pol)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -830,6 +830,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         fast_tiles = f < 0 ? 0 : (f > nhalf ? nhalf : (int)f);
       }
       const float2* const fast_src = A.iq + sg.offset - (DECIM - 1) - odd;
+      const unsigned long long pol = l2_policy_evict_first();   // every raw sample is read exactly once
       FusedArgs FA;  // issue_tile_load only reads iq / n_raw
       FA.iq = A.iq; FA.n_raw = A.n_raw;
       for (int k = 0; k < nhalf; k++) {
@@ -838,7 +839,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
         float2* dst = raw + (size_t)rs_ * A.raw_stage_samples;
         if (k >= 1 && k < fast_tiles) {
           mbar_arrive_expect_tx(&B.raw_full[rs_], fast_bytes);
-          tma_load_1d(dst, fast_src + (size_t)k * (DECIM * kTT), fast_bytes, &B.raw_full[rs_]);
+          tma_load_1d_hint(dst, fast_src + (size_t)k * (DECIM * kTT), fast_bytes, &B.raw_full[rs_], pol);
         } else {
           issue_tile_load<DECIM>(FA, sg, k, dst, &B.raw_full[rs_]);
         }

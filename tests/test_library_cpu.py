@@ -117,6 +117,6 @@ def test_sass_of_the_new_kernels_is_present():
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
     out = subprocess.check_output(["cuobjdump", "-sass", capi.LIB], text=True)
-    for k in ("ingest_mask", "ingest_scan", "ingest_bursts", "tx_synth_kernel", "sim_slot_kernel", "rx_fused_split_kernel"):
+    for k in ("ingest_mask", "ingest_scan", "ingest_bursts", "tx_synth_kernel", "sim_slot_kernel", "rx_fused_split_kernel", "rx_pack_kernel"):
         assert k in out, k
     assert "FMNMX3" in out and "FADD2" in out      # 3-input min/max range test, packed f32x2 adds of the worker
