@@ -142,6 +142,17 @@ int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 bool fast_path_ok(const RxConfig& c) { return c.win_length <= kTT && c.dc_length <= kTT; }
 
+// smallest decoder stage for a window that is complete when the decode starts: the head (sync range + 6 symbols) and one
+// chunk of the symbol-period search (one float per sample); the bit decisions and the rest of an RN16 window are read from
+// global memory directly
+int decode_stage_small(const RxConfig& c)
+{
+  const int head = c.sync_range + (int)(6.0f * c.n_tag_bit_f) + 2;
+  const int span = (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8;
+  int need = head > (span + 1) / 2 ? head : (span + 1) / 2;
+  return align_up(need, 8);
+}
+
 // shared-memory carve-up of rx_fused_split_kernel: five tile stages forming one time-indexed ring
 void make_layout_split(const RxConfig& c, FusedArgs& L)
 {
@@ -189,6 +200,9 @@ void make_layout(const RxConfig& c, FusedArgs& L)
     L.off_ycl = off; off = align_up(off + L.ycl_size * 8, 16);
     L.off_e = off; off += 2 * (kTT + 16) * 4;
   }
+  // (long rings leave little shared memory: the decoder stages the window's head only and gathers the rest from L2)
+  L.dstage_samples = align_up(c.sync_range + (int)(6.0f * c.n_tag_bit_f) + 2, 8);
+  L.off_dstage = off; off = align_up(off + L.dstage_samples * 8, 16);
   L.rn16_pad = align_up(c.len_rn16, 16);
   L.win_stride = L.rn16_pad + align_up(c.len_epc, 16);
   L.smem_bytes = off;
@@ -220,15 +234,9 @@ void make_layout_pack(const RxConfig& c, int G, PackArgs& L)
   L.o_raw = o; o = align_up(o + 2 * L.raw_stage_samples * 8, 16);
   L.o_tail_y = o; o = align_up(o + 2 * c.dc_length * 8, 16);
   L.o_ring_a = o; o += kRingA * 4;
-  // decode stage: an RN16 window is staged whole; an EPC window needs its head (sync range + 6 symbols) and one chunk of
-  // the symbol-period search (one float per sample) -- the bit decisions read the history directly
-  {
-    const int head = c.sync_range + (int)(6.0f * c.n_tag_bit_f) + 2;
-    const int span = (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8;
-    int need = c.len_rn16 > head ? c.len_rn16 : head;
-    if (need < (span + 1) / 2) need = (span + 1) / 2;
-    L.dstage_samples = align_up(need, 8);
-  }
+  // decode stage: an RN16 window is staged whole; an EPC window needs its head and one chunk of the period search
+  L.dstage_samples = decode_stage_small(c);
+  if (L.dstage_samples < c.len_rn16) L.dstage_samples = align_up(c.len_rn16, 8);
   L.o_dstage = o; o = align_up(o + L.dstage_samples * 8, 16);
   L.seg_bytes = o;
   int off = 0;

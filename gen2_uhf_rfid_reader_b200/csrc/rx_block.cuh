@@ -124,13 +124,9 @@ __global__ void __launch_bounds__(32) gate_block_kernel(RxConfig C, GateState* s
 __global__ void __launch_bounds__(32) decode_block_kernel(RxConfig C, int kind, const float2* __restrict__ win_g, int n,
                                                           rfid_b200_window_result* res)
 {
-  extern __shared__ __align__(16) unsigned char dsm[];
-  float2* w = reinterpret_cast<float2*>(dsm);
-  float* M = reinterpret_cast<float*>(w + n);
-  for (int i = threadIdx.x; i < n; i += 32) w[i] = win_g[i];
-  __syncwarp();
+  extern __shared__ __align__(16) unsigned char dsm[];   // 12 n + 64 bytes: a decoder stage of 1.5 n samples
   WindowDecode wd;
-  decode_window_warp<false>(C, kind, w, n, M, wd);
+  decode_window_staged(C, kind, win_g, n, reinterpret_cast<float2*>(dsm), n + n / 2, wd);
   if (threadIdx.x == 0)
     store_result(res, wd, 0, 0, 0, kind == RFID_B200_RN16 ? C.len_rn16 : C.len_epc, kind);
 }

@@ -47,173 +47,13 @@ __device__ __forceinline__ int crc16_check(const uint32_t bits[4])
   return rcvd == crc ? 1 : 0;
 }
 
-// w: window samples (y - dc_est), n_avail samples; M: scratch for |w|^2 (EPC only, >= n_avail floats).
-// All 32 lanes of the warp must call; the result is valid in every lane.
-// M == nullptr: |w|^2 is evaluated at every gather of the period search instead of being staged.
-// GLOBAL_W: the window lives in global memory (L2-resident scratch written by another warp of this CTA):
-// read it with ld.global.cg so that no stale L1 line can be observed.
-// SUB_DC: the buffer holds the matched filter's output y and the gate's DC estimate is removed here, at every load
-// (y - dc_est is one exact float subtraction per component, gate_impl.cc:173,187, wherever it is evaluated).
-template <bool GLOBAL_W, bool SUB_DC = false>
-struct WinView {
-  const float2* p;
-  float2 dc;
-  __device__ __forceinline__ float2 operator[](int i) const
-  {
-    const float2 v = GLOBAL_W ? __ldcg(p + i) : p[i];
-    return SUB_DC ? c_sub(v, dc) : v;
-  }
-};
-
-template <bool GLOBAL_W, bool SUB_DC = false>
-__device__ __forceinline__ void decode_window_warp(const RxConfig& c, int kind, const float2* __restrict__ w_ptr,
-                                                   int n_avail, float* __restrict__ M, WindowDecode& out,
-                                                   float2 dc = make_float2(0.f, 0.f))
-{
-  const WinView<GLOBAL_W, SUB_DC> w{w_ptr, dc};
-  const int lane = threadIdx.x & 31;
-  const float n = c.n_tag_bit_f;
-
-  // ---- tag_sync (tag_decoder_impl.cc:85-100): sync_range offsets x 12 taps, first strict max from 0
-  float best = -1.0f;
-  int best_i = 0x7fffffff;
-  for (int i = lane; i < c.sync_range; i += 32) {
-    float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int j = 0; j < 2 * kTagPreambleBits; j++) {
-      int k = (int)f_add((float)i, f_div(f_mul((float)j, n), 2.0f));  // (int)(i + j*n/2), :92
-      float2 s = w[k];
-      float cr = (float)((kPreambleMask >> j) & 1u);
-      // in[k] * gr_complex(P[j], 0)  ->  (a*c - b*0, a*0 + b*c)
-      float pr = f_sub(f_mul(s.x, cr), f_mul(s.y, 0.0f));
-      float pi = f_add(f_mul(s.x, 0.0f), f_mul(s.y, cr));
-      acc.x = f_add(acc.x, pr);
-      acc.y = f_add(acc.y, pi);
-    }
-    float corr = c_norm(acc);
-    if (corr > best) {  // per-lane candidates ascend in i, so strict > keeps the first
-      best = corr;
-      best_i = i;
-    }
-  }
-  warp_argmax_first(best, best_i);
-  int max_index = 0;
-  float max_corr = 0.0f;
-  if (best > 0.0f) {  // `if (corr > max)` with max initialised to 0 (:81,95)
-    max_index = best_i;
-    max_corr = best;
-  }
-  // ---- h_est (:103)
-  {
-    int t1 = (int)f_add((float)max_index, f_div(n, 2.0f));
-    int t3 = (int)f_add((float)max_index, f_div(f_mul(3.0f, n), 2.0f));
-    int t6 = (int)f_add((float)max_index, f_div(f_mul(6.0f, n), 2.0f));
-    int t10 = (int)f_add((float)max_index, f_div(f_mul(10.0f, n), 2.0f));
-    int t11 = (int)f_add((float)max_index, f_div(f_mul(11.0f, n), 2.0f));
-    float2 s = w[max_index];
-    s = c_add(s, w[t1]);
-    s = c_add(s, w[t3]);
-    s = c_add(s, w[t6]);
-    s = c_add(s, w[t10]);
-    s = c_add(s, w[t11]);
-    out.h = make_float2(f_div(s.x, 6.0f), f_div(s.y, 6.0f));
-  }
-  out.sync_index = max_index;
-  out.score = max_corr;
-  // :107  max_index + TAG_PREAMBLE_BITS * n + n/2, truncated
-  const int index = (int)f_add(f_add((float)max_index, f_mul((float)kTagPreambleBits, n)), f_div(n, 2.0f));
-  const float2 h = out.h;
-  out.bits[0] = out.bits[1] = out.bits[2] = out.bits[3] = 0u;
-
-  if (kind == RFID_B200_RN16) {
-    // ---- half-bit sampling (:237-253): j_m = index + m*(n/2) accumulated in float (exact here)
-    const float half = f_div(n, 2.0f);
-    const int want = 2 * (kRN16Bits - 1);  // 32 samples
-    float jm = (float)index;
-    for (int m = 0; m < lane; m++) jm = f_add(jm, half);
-    bool have = jm < (float)n_avail;
-    unsigned have_mask = __ballot_sync(0xffffffffu, have);
-    float2 s = make_float2(0.0f, 0.0f);
-    if (have) s = w[(int)roundf(jm)];
-    out.T = 0.0f;
-    out.crc_ok = -1;
-    if (have_mask == 0xffffffffu && want == 32) {
-      // ---- tag_detection_RN16 (:121-140)
-      float2 s_next = make_float2(__shfl_down_sync(0xffffffffu, s.x, 1), __shfl_down_sync(0xffffffffu, s.y, 1));
-      float res = c_proj(s, s_next, h);
-      unsigned pos = __ballot_sync(0xffffffffu, res > 0.0f);
-      // keep even lanes (pair j = lanes 2j, 2j+1), compact to 16 sign bits
-      unsigned S = 0;
-#pragma unroll
-      for (int j = 0; j < 16; j++) S |= ((pos >> (2 * j)) & 1u) << j;
-      // bit_j = (sign_j != sign_{j-1}), sign_{-1} = positive
-      unsigned B = (S ^ ((S << 1) | 1u)) & 0xFFFFu;
-      unsigned msb = 0;
-#pragma unroll
-      for (int j = 0; j < 16; j++) msb |= ((B >> j) & 1u) << (31 - j);
-      out.bits[0] = msb;
-      out.tag_id = (int)(msb >> 16);
-    } else {
-      out.crc_ok = -2;  // window too short for 32 half bits: the branch at :269-288
-      out.tag_id = -1;
-    }
-    return;
-  }
-
-  // ---- EPC: magn_squared_samples (gate_impl.cc:172,186)
-  if (M) {
-    for (int p = lane; p < n_avail; p += 32) M[p] = c_norm(w[p]);
-    __syncwarp();
-  }
-  // ---- symbol-period search (:151-165): 20 candidates, 256 sequential gathers each
-  const int number_steps = 20;
-  const float min_val = c.t_min, max_val = c.t_max;
-  float energy = -1.0f;
-  int e_idx = 0x7fffffff;
-  if (lane < number_steps) {
-    const float Tt = f_add(min_val, f_div(f_mul((float)lane, f_sub(max_val, min_val)), (float)(number_steps - 1)));
-    float e = 0.0f;
-#pragma unroll 16
-    for (int i = 0; i < 256; i++) {
-      int p = (int)f_add(f_mul((float)i, Tt), (float)index);  // :161
-      e = f_add(e, M ? M[p] : c_norm(w[p]));
-    }
-    energy = e;
-    e_idx = lane;
-  }
-  // std::max_element: first largest (NaN never wins a `<` comparison; energies here are finite)
-  warp_argmax_first(energy, e_idx);
-  const int index_T = e_idx;
-  const float T = f_add(min_val, f_div(f_mul((float)index_T, f_sub(max_val, min_val)), (float)(number_steps - 1)));  // :166
-  out.T = T;
-  // ---- 128 bit decisions (:171-191)
-  const float twoT = f_mul(2.0f, T);
-  unsigned S[4];
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    int j = r * 32 + lane;
-    int a = (int)f_add(f_mul((float)j, twoT), (float)index);                       // j*(2*T) + index
-    int b = (int)f_add(f_add(f_mul((float)(j * 2), T), T), (float)index);          // j*2*T + T + index
-    float res = c_proj(w[a], w[b], h);
-    S[r] = __ballot_sync(0xffffffffu, res > 0.0f);  // bit lane = sign of pair j
-  }
-  // bit_j = sign_j ^ sign_{j-1}, sign_{-1} = 1
-  unsigned carry = 1u;
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    unsigned prev = (S[r] << 1) | carry;
-    carry = S[r] >> 31;
-    unsigned B = S[r] ^ prev;                 // bit lane = message bit 32r + lane
-    out.bits[r] = __brev(B);                  // MSB first
-  }
-  out.crc_ok = crc16_check(out.bits);
-  out.tag_id = (int)((out.bits[3] >> 16) & 0xFFu);  // byte 13 = bits[104..111] (:348-352)
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// Staged variant for a window that lives in global memory (the fused kernel's L2-resident scratch): the warp
-// copies the part of the window it is about to use into a small shared-memory stage with coalesced loads and
-// runs the same arithmetic as decode_window_warp from there.  stage_cap >= decode_stage_samples(n_tag_bit).
+// The decoder of one window (tag_decoder_impl.cc:78-191, 223-393), ONE copy for every kernel: the window lives in global
+// memory (a capture kernel's L2-resident scratch / history, or the block-mode input buffer); the warp copies the part of
+// the window it is about to use into a small shared-memory stage with coalesced loads and gathers from there.
+// w = y - dc_est: dc is subtracted as the samples are loaded (one exact float subtraction, gate_impl.cc:173,187).
+// All 32 lanes of the warp must call; the result is valid in every lane.  The stage must hold the window head (sync range +
+// 6 symbols); with room for a chunk of the symbol-period search the search runs from the stage, else it gathers from L2.
 __host__ __device__ inline int decode_stage_samples(float n_tag_bit)
 {
   // one chunk = 32 consecutive bit pairs: 31 symbols + one half symbol at the longest candidate period, + slack
@@ -523,8 +363,32 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
     // (Tried: all 32 lanes gathering 16 steps x 20 candidates into a table that lane t then adds up in order -- fewer
     // instructions, but slower than the plain loop below: 19.6 k vs 15.6 k cycles per window.)
     float* stage_m = reinterpret_cast<float*>(stage);
-    const int span = min(2 * stage_cap, (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8);
-    if (span <= 32 * kFillBatch) {
+    const int span_full = (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8;
+    const int span = min(2 * stage_cap, span_full);
+    if (span_full > 2 * stage_cap) {
+      // the stage holds the head only (kernels whose shared memory is spoken for): |w|^2 straight from global memory,
+      // eight gathers in flight, added in order
+      if (lane < 20) {
+        const float findex = (float)index, Tt = S.Tt;
+        float e = S.e;
+#pragma unroll 1
+        for (int i = kChunkSteps * (S.phase - 1); i < kChunkSteps * kSearchChunks; i += 8) {
+          const float fi = (float)i;
+          float2 g8[8];
+          bool in8[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int p = (int)f_add(f_mul(f_add(fi, (float)u), Tt), findex);  // (int)(i * T + index), :161
+            in8[u] = p >= 0 && p < n_avail;
+            g8[u] = in8[u] ? __ldcg(gw.at(p)) : dc;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) e = f_add(e, in8[u] ? c_norm(c_sub(g8[u], dc)) : 0.0f);
+        }
+        S.e = e;
+      }
+      S.phase = kSearchChunks + 1;
+    } else if (span <= 32 * kFillBatch) {
       // chunk k+1's samples travel from L2 into registers while chunk k's 64 steps run from the stage
       float2 v[kFillBatch];
       int lo = (int)f_add(f_mul((float)(kChunkSteps * (S.phase - 1)), c.t_min), (float)index);

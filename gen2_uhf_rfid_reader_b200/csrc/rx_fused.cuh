@@ -86,7 +86,7 @@ struct FusedArgs {
   float2* window_tap;            // optional: ungated samples of every stored window (stride len_epc)
   float2* win_scratch;           // [nseg][win_stride]: the window being decoded (RN16 at 0, EPC at rn16_pad); L2-resident
   int win_stride, rn16_pad;
-  int off_dstage, dstage_samples; // decoder staging buffer (split kernel)
+  int off_dstage, dstage_samples; // decoder staging buffer
   RxConfig cfg;
   // shared-memory carve-up (bytes from the dynamic smem base), computed on the host
   int off_raw, raw_stage_samples;
@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
   // ungated window samples go to a per-segment global scratch (written once, read once by the decoder warp
   // of the same CTA a few microseconds later: L2 traffic, not shared memory -- that is what lets 8 CTAs fit an SM)
   float2* const win_base = A.win_scratch + (size_t)seg * A.win_stride;
+  float2* const dstage = reinterpret_cast<float2*>(smem + A.off_dstage);  // decoder's staging buffer
 
   // ---- init: zero the history rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56;
   //      x[<0] = +0 for the matched filter), set up the TMA barriers
@@ -568,7 +569,7 @@ __global__ void __launch_bounds__(kFusedThreads, 8) rx_fused_kernel(const FusedA
       const int ordinal = B.meta_ordinal[j & 1], open_idx = B.meta_open[j & 1], len = B.meta_len[j & 1];
       WindowDecode wd;
       const float2* win = win_base + (kind ? A.rn16_pad : 0);
-      decode_window_warp<true>(C, kind, win, len, nullptr, wd);
+      decode_window_staged(C, kind, win, len, dstage, A.dstage_samples, wd);
       rfid_b200_window_result* dst = A.results + (size_t)seg * A.max_windows + ordinal;
       if (lane == 0) store_result(dst, wd, seg + A.seg_base, ordinal, open_idx, len, kind);
 #ifndef RFID_B200_PHASE_PROFILE
