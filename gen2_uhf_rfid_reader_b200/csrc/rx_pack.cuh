@@ -6,29 +6,32 @@
 //     matched filter, |y|, ring differences (or thresholds + the edge / pulse state machine) needs 2-3 thousand cycles per
 //     pass almost independently of how many samples the pass covers;
 //   * the stages of a segment have very different costs from tile to tile (the state machine costs 1 k cycles on a
-//     carrier-only tile and 5 k on a tile full of reader pulses), so a lockstep hand-off per tile runs at the sum of the
+//     carrier-only tile and 6 k on a tile full of reader pulses), so a lockstep hand-off per tile runs at the sum of the
 //     worst stages.
 // So a CTA owns G <= kPMaxSeg capture segments, one warp per role and segment, ONE chain warp for all of them, and the
 // stages are coupled only through small rings with full / free barriers (mbarriers, one phase per slot use):
 //   warp A0/A1[g] P1: waits for the raw half-tile (TMA bulk copies issued by the loader warp), block-sum matched filter,
 //               exact |y|, amplitude / DC ring differences of 4 outputs per lane.  Writes |y| and the amplitude quotients
-//               into 3-slot rings, the DC quotients into a 4-slot ring, and y itself into the segment's circular history in
-//               global memory (L2 resident, kYW samples).  May run up to three tiles ahead of warp B.
-//   chain warp  lane 8*c + g replays running sum c (0 avg_ampl, 1 dc_est.re, 2 dc_est.im) of segment g: avg_ampl of tile j
-//               as soon as every segment's P1(j) is in, dc_est of tile j-2 once every segment's P3(j-2) has fixed its list;
-//               then hands dc_est at every window's trigger sample to warp C.
-//   warp B[g]   P3: thresholds by ballot, the edge / pulse state machine on 256-bit masks spread over 8 lanes, the DC-ring
-//               differences around gate activity (y read back from the history).  Frees the |y| / quotient slot as soon as
-//               its masks are made.  Registers opening / closing windows in a small queue.
-//   warp C[g]   decodes every closed window straight from the history (rx_decode.cuh); dc_est is subtracted as the
-//               decoder reads the samples -- the same exact float subtraction, gate_impl.cc:173,187.
+//               into 4-slot rings, the DC quotients into a 5-slot ring, and y itself into the segment's circular history in
+//               global memory (L2 resident, kYW samples).  May run up to four tiles ahead of warp B.
+//   chain warp  lane 8*c + g replays running sum c (0 avg_ampl, 1 dc_est.re, 2 dc_est.im) of segment g: avg_ampl of tile i
+//               as soon as every segment's P1(i) is in, dc_est of tile j once every segment's P3(j) has fixed its list --
+//               whichever is ready, both in one pass when both are; then hands dc_est at every window's trigger sample
+//               to warp C.
+//   warp B[g]   P3: thresholds by ballot (one mask word per lane), the edge / pulse state machine on the 256-bit masks, the
+//               DC-tracker inputs of the 48 samples after a window (y read back from the history), -0.0f for the samples
+//               inside windows.  Frees the |y| / quotient slot as soon as its masks are made.  Queues opening windows.
+//   warp C[g]   decodes every queued window straight from the history as soon as its last sample and its dc_est exist
+//               (rx_decode.cuh); dc_est is subtracted as the decoder reads the samples -- the same exact float
+//               subtraction, gate_impl.cc:173,187.
 //   loader      lane g streams segment g's raw samples through its two half-tile stages as warp A frees them.
 // The history is indexed by the SM (one CTA per SM: the shared-memory request guarantees it), so its size does not depend
 // on the number of segments of the launch; warp A never overwrites a sample a queued window still needs.
-// Shared memory per segment: 2 raw half-tile stages (10 KB), the last dc_length outputs of either half-tile (P1's DC lookback
-// is a lane shuffle plus this tail), a 4-tile ring of |y| (4 KB); per CTA the running-sum buffers (4 + 5x2 per segment,
-// 1072 B each, skewed so the chain warp's 128-bit accesses are bank-conflict free).  HBM traffic: every raw sample is read once, 64 B are written per window; the history
-// (8 B per decimated sample, rewritten in place) lives in L2.
+// Shared memory per segment: 2 raw half-tile stages (10 KB), the last dc_length outputs of either half-tile (P1's DC
+// lookback is a lane shuffle plus this tail), a 4-tile ring of |y| (4 KB), the decoder's stage (2 KB); per CTA the
+// running-sum buffers (4 + 5x2 per segment, 1072 B each, skewed so the chain warp's 128-bit accesses are bank-conflict
+// free).  HBM traffic: every raw sample is read once (evict-first), 64 B are written per window; the history (8 B per
+// decimated sample, rewritten in place) lives in L2.
 #pragma once
 
 #include "rx_fused_split.cuh"
