@@ -72,6 +72,7 @@ struct PackArgs {
 };
 
 struct PackSegCtl {
+  rfid_b200_segment seg;     // the segment's table entry (length 0: none), read from global memory once per CTA
   uint64_t raw_full[2];      // loader (TMA transaction count) -> warp A
   uint64_t raw_empty[2];     // warps A (stage 0: A0 and A1's halo read, stage 1: A1) -> loader
   uint64_t half_rdy;         // warp A0 -> warp A1: y and |y| of the first half-tile are in the rings
@@ -255,26 +256,36 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
   float* const dA = reinterpret_cast<float*>(smem + A.off_dA);   // [kPAS][G][kPChainBuf]
   float* const dD = reinterpret_cast<float*>(smem + A.off_dD);   // [kPDS][2][G][kPChainBuf]
 
-  // ---- init: barriers first, so that the loader warp can start the first raw half-tiles on their way while the other
-  // warps zero the time rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56)
-  if (threadIdx.x < G) {
-    PackSegCtl& c = ctl_all[threadIdx.x];
-    for (int s = 0; s < 2; s++) { mbar_init(&c.raw_full[s], 1); mbar_init(&c.raw_empty[s], s == 0 ? 2 : 1); }
-    mbar_init(&c.half_rdy, 1); mbar_init(&c.tail_rdy, 1);
-    for (int s = 0; s < kPAS; s++) mbar_init(&c.freeA[s], 1);
-    for (int m = 0; m < 4; m++) { c.keep[0][m] = make_float2(0.f, 0.f); c.keep[1][m] = make_float2(0.f, 0.f); }
-    for (int s = 0; s < kPDS; s++) { c.n_e[s] = 0; c.trig_n[s] = 0; }
-    c.n_opened = 0; c.n_dc = 0; c.n_decoded = 0; c.seg_done = 0; c.y_tiles = 0;
-    c.b_wcount = 0; c.b_nq = 1; c.b_snap_base = 0; c.b_queued = 0;
-  }
-  if (threadIdx.x == 32) {
-    for (int s = 0; s < kPAS; s++) { mbar_init(&cta.fullA[s], 2 * G); mbar_init(&cta.avgdone[s], 1); }
-    for (int s = 0; s < kPDS; s++) { mbar_init(&cta.p3done[s], G); mbar_init(&cta.dcdone[s], 1); }
-  }
-  if (threadIdx.x < G || threadIdx.x == 32) mbar_fence_init();
-  __syncthreads();
+  // ---- init.  The loader warp initialises the raw-stage barriers itself and sends the first two half-tiles of every
+  // segment on their way before it joins the start-up barrier; meanwhile the other warps initialise the hand-off barriers,
+  // zero the rings (win_samples / dc_samples start at 0, gate_impl.cc:55-56) and read the segment lengths.
   int max_tiles = 0;
-  if (warp != 3 * G) {
+  if (warp == 3 * G) {
+    if (lane < G) {
+      PackSegCtl& c = ctl_all[lane];
+      for (int s = 0; s < 2; s++) { mbar_init(&c.raw_full[s], 1); mbar_init(&c.raw_empty[s], s == 0 ? 2 : 1); }
+      mbar_fence_init();
+    }
+    __syncwarp();
+  } else {
+    rfid_b200_segment sg0;       // (threads 0..G-1: the load is in flight while the barriers are initialised and the rings zeroed)
+    sg0.offset = 0; sg0.length = 0; sg0.reserved = 0;
+    if ((int)threadIdx.x < g_act) sg0 = A.segs[seg0 + threadIdx.x];
+    if (threadIdx.x < G) {
+      PackSegCtl& c = ctl_all[threadIdx.x];
+      mbar_init(&c.half_rdy, 1); mbar_init(&c.tail_rdy, 1);
+      for (int s = 0; s < kPAS; s++) mbar_init(&c.freeA[s], 1);
+      for (int m = 0; m < 4; m++) { c.keep[0][m] = make_float2(0.f, 0.f); c.keep[1][m] = make_float2(0.f, 0.f); }
+      for (int s = 0; s < kPDS; s++) { c.n_e[s] = 0; c.trig_n[s] = 0; }
+      c.n_opened = 0; c.n_dc = 0; c.n_decoded = 0; c.seg_done = 0; c.y_tiles = 0;
+      c.b_wcount = 0; c.b_nq = 1; c.b_snap_base = 0; c.b_queued = 0;
+      mbar_fence_init();
+    }
+    if (threadIdx.x == 32) {
+      for (int s = 0; s < kPAS; s++) { mbar_init(&cta.fullA[s], 2 * G); mbar_init(&cta.avgdone[s], 1); }
+      for (int s = 0; s < kPDS; s++) { mbar_init(&cta.p3done[s], G); mbar_init(&cta.dcdone[s], 1); }
+      mbar_fence_init();
+    }
     for (int g = 0; g < G; g++) {
       unsigned char* sb = smem + A.off_seg + (size_t)g * A.seg_bytes;
       float4* ry = reinterpret_cast<float4*>(sb + A.o_tail_y);
@@ -283,12 +294,13 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
       for (int i = tid; i < C.dc_length; i += nth) ry[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // two tails of dc_length samples
       for (int i = tid; i < kRingA / 4; i += nth) ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (threadIdx.x < G) ctl_all[threadIdx.x].seg = sg0;
+    asm volatile("bar.sync 14, %0;" ::"r"((int)blockDim.x) : "memory");   // start-up barrier (the loader joins it below)
     // the CTA's barriers count every warp A / B for every tile of the longest segment
     for (int g = 0; g < g_act; g++) {
-      const int n_out_g = (int)(A.segs[seg0 + g].length / DECIM);
+      const int n_out_g = (int)(ctl_all[g].seg.length / DECIM);
       max_tiles = max(max_tiles, (n_out_g + kT2 - 1) / kT2);
     }
-    asm volatile("bar.sync 15, %0;" ::"r"((int)blockDim.x - 32) : "memory");   // everybody but the loader warp
   }
 
   if (warp < 3 * G) {
@@ -300,7 +312,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     const int seg = seg0 + g;
     rfid_b200_segment sg;
     sg.offset = 0; sg.length = 0; sg.reserved = 0;
-    if (have) sg = A.segs[seg];
+    if (have) sg = ctl_all[g].seg;
     const int n_out = (int)(sg.length / DECIM);
     const int ntiles = (n_out + kT2 - 1) / kT2;
     PackSegCtl& B = ctl_all[g];
@@ -747,7 +759,7 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     const int comp = lane >> 3, g = lane & 7;
     const bool active = comp < 3 && g < g_act;
     int n_out = 0;
-    if (active) n_out = (int)(A.segs[seg0 + g].length / DECIM);
+    if (active) n_out = (int)(ctl_all[g].seg.length / DECIM);
     float acc = 0.f;
     PP_DECL
 #ifdef RFID_B200_PHASE_PROFILE
@@ -812,41 +824,48 @@ __global__ void __launch_bounds__(kPackMaxThreads, 1) rx_pack_kernel(const PackA
     }
   } else if (warp == 3 * G) {
     // ======================================================================================= loader warp
-    // lane g streams the raw half-tiles of segment g through its two stages (TMA bulk copies) as warp A frees them
+    // lane g streams the raw half-tiles of segment g through its two stages (TMA bulk copies) as warp A frees them; the
+    // first two go out before the start-up barrier
     const int g = lane;
-    if (g < g_act) {
-      const rfid_b200_segment sg = A.segs[seg0 + g];
-      const int n_out = (int)(sg.length / DECIM);
-      const int nhalf = (n_out + kTT - 1) / kTT;
-      PackSegCtl& B = ctl_all[g];
-      float2* raw = reinterpret_cast<float2*>(smem + A.off_seg + (size_t)g * A.seg_bytes + A.o_raw);
-      // raw half-tile geometry (as rx_fused_split.cuh)
-      const int odd = (int)(sg.offset & 1ull);
-      const uint32_t fast_bytes = (uint32_t)((DECIM * kTT + 2 * odd) * 8);
-      int fast_tiles = 0;
-      {
-        const long long by_len = ((long long)sg.length - 1 - (long long)DECIM * (kTT - 1)) / ((long long)DECIM * kTT);
-        const long long room = (long long)A.n_raw - (long long)sg.offset + (DECIM - 1) + odd - (DECIM * kTT + 2 * odd);
-        const long long by_buf = room >= 0 ? room / ((long long)DECIM * kTT) : -1;
-        long long f = (by_len < by_buf ? by_len : by_buf) + 1;
-        if (sg.length < (unsigned)(DECIM * kTT)) f = 0;
-        fast_tiles = f < 0 ? 0 : (f > nhalf ? nhalf : (int)f);
+    rfid_b200_segment sg;
+    sg.offset = 0; sg.length = 0; sg.reserved = 0;
+    if (g < g_act) sg = A.segs[seg0 + g];
+    const int n_out = (int)(sg.length / DECIM);
+    const int nhalf = g < g_act ? (n_out + kTT - 1) / kTT : 0;
+    PackSegCtl& B = ctl_all[g < G ? g : 0];
+    float2* raw = reinterpret_cast<float2*>(smem + A.off_seg + (size_t)(g < G ? g : 0) * A.seg_bytes + A.o_raw);
+    // raw half-tile geometry (as rx_fused_split.cuh)
+    const int odd = (int)(sg.offset & 1ull);
+    const uint32_t fast_bytes = (uint32_t)((DECIM * kTT + 2 * odd) * 8);
+    int fast_tiles = 0;
+    {
+      const long long by_len = ((long long)sg.length - 1 - (long long)DECIM * (kTT - 1)) / ((long long)DECIM * kTT);
+      const long long room = (long long)A.n_raw - (long long)sg.offset + (DECIM - 1) + odd - (DECIM * kTT + 2 * odd);
+      const long long by_buf = room >= 0 ? room / ((long long)DECIM * kTT) : -1;
+      long long f = (by_len < by_buf ? by_len : by_buf) + 1;
+      if (sg.length < (unsigned)(DECIM * kTT)) f = 0;
+      fast_tiles = f < 0 ? 0 : (f > nhalf ? nhalf : (int)f);
+    }
+    const float2* const fast_src = A.iq + sg.offset - (DECIM - 1) - odd;
+    FusedArgs FA;  // issue_tile_load only reads iq / n_raw
+    FA.iq = A.iq; FA.n_raw = A.n_raw;
+    const unsigned long long pol = l2_policy_evict_first();   // every raw sample is read exactly once
+    auto issue = [&](int k) {
+      const int rs_ = k & 1;
+      float2* dst = raw + (size_t)rs_ * A.raw_stage_samples;
+      if (k >= 1 && k < fast_tiles) {
+        mbar_arrive_expect_tx(&B.raw_full[rs_], fast_bytes);
+        tma_load_1d_hint(dst, fast_src + (size_t)k * (DECIM * kTT), fast_bytes, &B.raw_full[rs_], pol);
+      } else {
+        issue_tile_load<DECIM>(FA, sg, k, dst, &B.raw_full[rs_]);
       }
-      const float2* const fast_src = A.iq + sg.offset - (DECIM - 1) - odd;
-      const unsigned long long pol = l2_policy_evict_first();   // every raw sample is read exactly once
-      FusedArgs FA;  // issue_tile_load only reads iq / n_raw
-      FA.iq = A.iq; FA.n_raw = A.n_raw;
-      for (int k = 0; k < nhalf; k++) {
-        const int rs_ = k & 1;
-        if (k >= 2) mbar_wait_idle(&B.raw_empty[rs_], (uint32_t)(((k >> 1) - 1) & 1), 100);
-        float2* dst = raw + (size_t)rs_ * A.raw_stage_samples;
-        if (k >= 1 && k < fast_tiles) {
-          mbar_arrive_expect_tx(&B.raw_full[rs_], fast_bytes);
-          tma_load_1d_hint(dst, fast_src + (size_t)k * (DECIM * kTT), fast_bytes, &B.raw_full[rs_], pol);
-        } else {
-          issue_tile_load<DECIM>(FA, sg, k, dst, &B.raw_full[rs_]);
-        }
-      }
+    };
+    for (int k = 0; k < 2 && k < nhalf; k++) issue(k);   // both stages are free at the start
+    __syncwarp();
+    asm volatile("bar.sync 14, %0;" ::"r"((int)blockDim.x) : "memory");   // start-up barrier
+    for (int k = 2; k < nhalf; k++) {
+      mbar_wait_idle(&B.raw_empty[k & 1], (uint32_t)(((k >> 1) - 1) & 1), 100);
+      issue(k);
     }
   } else {
     // ======================================================================================= warp C: decode
