@@ -50,6 +50,9 @@ struct rfid_b200_ctx {
   void* d_cnt; size_t d_cnt_bytes;
   void* d_win; size_t d_win_bytes;  // per-segment window scratch of the one-CTA-per-segment kernels
   void* d_yhist;                     // rx_pack_kernel: y history, [%nsmid][kPMaxSeg][kYW] float2
+  cudaEvent_t ev_hist;               // recorded after every rx_pack_kernel launch: the history serves one launch at a time
+  cudaStream_t hist_stream;          // stream of the last rx_pack_kernel launch
+  bool hist_used;
   // block mode
   GateState* d_gate;
   GateCallOut* d_gate_out;
@@ -344,6 +347,7 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
   ctx->d_iq = ctx->d_segs = ctx->d_res = ctx->d_cnt = ctx->d_in = ctx->d_out = ctx->d_m2 = ctx->d_mf = nullptr;
   ctx->d_win = nullptr; ctx->d_win_bytes = 0;
   ctx->d_yhist = nullptr;
+  ctx->ev_hist = nullptr; ctx->hist_stream = nullptr; ctx->hist_used = false;
   ctx->d_blk = nullptr; ctx->d_blk_bytes = 0; ctx->h_blk = nullptr; ctx->h_blk_bytes = 0;
   ctx->d_iq_bytes = ctx->d_segs_bytes = ctx->d_res_bytes = ctx->d_cnt_bytes = ctx->d_in_bytes = ctx->d_out_bytes = ctx->d_m2_bytes = ctx->d_mf_bytes = 0;
   ctx->d_gate = nullptr; ctx->d_gate_out = nullptr; ctx->d_one = nullptr;
@@ -393,6 +397,7 @@ int rfid_b200_create(const rfid_b200_params* p, rfid_b200_ctx** out)
     }
     if (e == cudaSuccess && nsmid < (unsigned)prop.multiProcessorCount) nsmid = prop.multiProcessorCount;
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_yhist, (size_t)nsmid * kPMaxSeg * kYW * sizeof(float2));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_hist, cudaEventDisableTiming);
   }
   if (e == cudaSuccess && pack_ok(cfg)) {
     PackArgs pl;
@@ -437,6 +442,7 @@ void rfid_b200_destroy(rfid_b200_ctx* ctx)
     if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
   }
   for (int k = 0; k < 4; k++) if (ctx->ev_slice[k]) cudaEventDestroy(ctx->ev_slice[k]);
+  if (ctx->ev_hist) cudaEventDestroy(ctx->ev_hist);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -542,7 +548,11 @@ static int decode_capture_impl(rfid_b200_ctx* ctx, const float* d_iq, size_t n_r
     P.iq = A.iq; P.n_raw = A.n_raw; P.segs = A.segs; P.nseg = nseg; P.seg_base = seg_base; P.max_windows = A.max_windows;
     P.results = A.results; P.counts = A.counts; P.window_tap = A.window_tap; P.y_hist = reinterpret_cast<float2*>(ctx->d_yhist);
     P.cfg = ctx->cfg;
+    // the y history belongs to one launch at a time: a launch on another stream than the previous one waits for it
+    if (ctx->hist_used && ctx->hist_stream != s) CK(cudaStreamWaitEvent(s, ctx->ev_hist, 0));
     rx_pack_kernel<5, 5><<<(nseg + P.G - 1) / P.G, 32 * (4 * P.G + 2), P.smem_bytes, s>>>(P);
+    CK(cudaEventRecord(ctx->ev_hist, s));
+    ctx->hist_stream = s; ctx->hist_used = true;
   } else {
     fn<<<nseg, fast_path_ok(ctx->cfg) ? kSplitThreads : kFusedThreads, A.smem_bytes, s>>>(A);
   }

@@ -587,6 +587,38 @@ def test_pack_kernel_any_segments_per_cta(oracle, g, monkeypatch):
     _assert_same(recs, orecs, "G=%d" % g)
 
 
+def test_one_context_two_streams_and_long_segments(oracle):
+    """rx_pack_kernel keeps the decimated-sample history of the segments in flight in ONE per-context scratch: launches of
+    the same context on different streams must serialise, and segments longer than the history (4096 decimated samples)
+    must wrap around it without losing a window -- both against the oracle"""
+    import torch
+    from gen2_uhf_rfid_reader_b200 import capi
+    dev = torch.device("cuda:0")
+    rx2 = capi.Gen2Rx()
+    caps = [synth.make_capture(300, seed=201 + k, device=dev) for k in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    outs = []
+    for k in range(2):   # back to back, no synchronisation in between
+        segs = capi.segments_to_device(caps[k]["segments"], dev)
+        outs.append((segs, rx2.decode_capture(caps[k]["iq"], segs, 4, stream=streams[k])))
+    torch.cuda.synchronize()
+    for k in range(2):
+        recs, counts = capi.results_to_numpy(outs[k][1][0], outs[k][1][1], 4)
+        orecs, ocounts, _ = oracle.decode_segments(caps[k]["iq"].cpu().numpy(), caps[k]["segments"], max_per_seg=4)
+        assert counts.tolist() == ocounts.tolist()
+        _assert_same(recs, orecs, "stream %d" % k)
+    # one segment = eight inventory rounds back to back: 27,136 decimated samples, 16 windows, six trips around the history
+    cap = synth.make_capture(24, seed=203)
+    iq = cap["iq"].numpy()
+    segs = cap["segments"][::8].copy()
+    segs["length"] = (8 * cap["segments"]["length"][0]).astype(np.uint32)
+    recs, counts = rx2.decode_capture_host(iq, segs, max_windows=16)
+    orecs, ocounts, _ = oracle.decode_segments(iq, segs, max_per_seg=16)
+    assert counts.tolist() == ocounts.tolist() and int(counts.max()) >= 12
+    _assert_same(recs, orecs, "long segments")
+
+
 def test_split_kernel_still_selectable(oracle, monkeypatch):
     """RFID_B200_KERNEL=split keeps the one-CTA-per-segment kernel for the reference configuration (A/B against the packed one)"""
     from gen2_uhf_rfid_reader_b200 import capi
