@@ -357,17 +357,15 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
   }
   if (!progress) {
     // ---- remaining chunks of the symbol-period search, whole window present (nobody to wait for): while chunk k's 64
-    // steps run from the stage, chunk k+1's cache lines travel from L2 into this SM's L1 (one touch per lane and line, the
-    // value is never used), so that its fill is a short trip.  The scratch was written by this warp before the decode began
-    // and an SM's own stores keep its L1 coherent; the streaming caller (progress != null) keeps the L2-only loads.
+    // steps run from the stage, chunk k+1's samples travel from L2 into registers; 16 gathers in flight, added in order.
     // (Tried: all 32 lanes gathering 16 steps x 20 candidates into a table that lane t then adds up in order -- fewer
     // instructions, but slower than the plain loop below: 19.6 k vs 15.6 k cycles per window.)
     float* stage_m = reinterpret_cast<float*>(stage);
     const int span_full = (int)((float)kChunkSteps * c.t_max + 256.0f * (c.t_max - c.t_min)) + 8;
     const int span = min(2 * stage_cap, span_full);
-    if (span_full > 2 * stage_cap) {
-      // the stage holds the head only (kernels whose shared memory is spoken for): |w|^2 straight from global memory,
-      // eight gathers in flight, added in order
+    if (span_full > 2 * stage_cap || span > 32 * kFillBatch) {
+      // the stage holds the head only (kernels whose shared memory is spoken for), or a chunk is longer than one load
+      // batch: |w|^2 straight from global memory, eight gathers in flight, added in order
       if (lane < 20) {
         const float findex = (float)index, Tt = S.Tt;
         float e = S.e;
@@ -388,7 +386,7 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
         S.e = e;
       }
       S.phase = kSearchChunks + 1;
-    } else if (span <= 32 * kFillBatch) {
+    } else {
       // chunk k+1's samples travel from L2 into registers while chunk k's 64 steps run from the stage
       float2 v[kFillBatch];
       int lo = (int)f_add(f_mul((float)(kChunkSteps * (S.phase - 1)), c.t_min), (float)index);
@@ -432,31 +430,6 @@ __device__ __forceinline__ void win_stream_finish(const RxConfig& c, int kind, c
         S.phase++;
       }
       __syncwarp();
-    } else {
-    while (S.phase <= kSearchChunks) {
-      const int i0 = kChunkSteps * (S.phase - 1);
-      const int lo = (int)f_add(f_mul((float)i0, c.t_min), (float)index);
-      stage_fill_l1<true>(stage_m, gw, lo, span, n_avail, dc, true);
-      float sink = 0.0f;
-      if (S.phase < kSearchChunks) sink = l1_touch_span(gw, (int)f_add(f_mul((float)(i0 + kChunkSteps), c.t_min), (float)index), span, n_avail);
-      if (lane < 20) {
-        const float findex = (float)index, Tt = S.Tt;
-        const float* sm = stage_m - lo;
-        float e = S.e;
-#pragma unroll 1
-        for (int i = i0; i < i0 + kChunkSteps; i += 16) {
-          const float fi = (float)i;
-          float v[16];
-#pragma unroll
-          for (int u = 0; u < 16; u++) v[u] = sm[(int)f_add(f_mul(f_add(fi, (float)u), Tt), findex)];  // (int)(i * T + index), :161
-#pragma unroll
-          for (int u = 0; u < 16; u++) e = f_add(e, v[u]);
-        }
-        S.e = e;
-      }
-      asm volatile("" ::"f"(sink));  // the touch may complete any time before here
-      S.phase++;
-    }
     }
   } else {
     while (S.phase <= kSearchChunks) win_stream_chunk(c, gw, n_avail, stage, stage_cap, dc, S, progress);
